@@ -1,0 +1,369 @@
+// extern "C" entry points declared in include/snb200.h.
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <fstream>
+
+#include "kernels.cuh"
+#include "net.h"
+
+using namespace snb;
+
+static thread_local char g_err[512] = {0};
+
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+static int fail(snb_ctx* c, int code, const char* msg) {
+  if (c) snprintf(c->err, sizeof(c->err), "%s", msg);
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+
+#define CK(c, expr)                                                                                 \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      snprintf((c)->err, sizeof((c)->err), "%s:%d %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      snprintf(g_err, sizeof(g_err), "%s", (c)->err);                                               \
+      return SNB_ERR_CUDA;                                                                          \
+    }                                                                                               \
+  } while (0)
+
+static void worker_main(snb_ctx* c);
+
+extern "C" {
+
+const char* snb_version(void) { return "snb200 0.1 (sm_100a)"; }
+
+const char* snb_last_error(const snb_ctx* ctx) { return ctx ? ctx->err : g_err; }
+
+int snb_create(snb_ctx** out, const snb_config* cfg) {
+  if (!out || !cfg || cfg->struct_size != (int32_t)sizeof(snb_config)) return fail(nullptr, SNB_ERR_INVALID, "snb_create: bad config struct");
+  *out = nullptr;
+  if (cfg->height <= 0 || cfg->width <= 0 || (cfg->height & 1) || (cfg->width & 1))
+    return fail(nullptr, SNB_ERR_INVALID, "snb_create: height and width must be positive and even (NV12)");
+  if (cfg->K < 1 || cfg->K > 5 || cfg->D < 1 || cfg->D > 512 || cfg->max_batch < 1)
+    return fail(nullptr, SNB_ERR_INVALID, "snb_create: need 1<=K<=5, 1<=D<=512, max_batch>=1");
+  if (cfg->precision != SNB_PREC_FP32 && cfg->precision != SNB_PREC_TC_F16X2)
+    return fail(nullptr, SNB_ERR_INVALID, "snb_create: unknown precision");
+
+  // model file check first, as SetNodePara does (stereonet_node.cpp:131-134)
+  std::vector<char> blob;
+  if (cfg->weights && cfg->weights_bytes) {
+    blob.assign((const char*)cfg->weights, (const char*)cfg->weights + cfg->weights_bytes);
+  } else {
+    if (!cfg->model_file || access(cfg->model_file, F_OK) != 0) {
+      snprintf(g_err, sizeof(g_err), "File is not exist! model_file: %s", cfg->model_file ? cfg->model_file : "(null)");
+      return SNB_ERR_MODEL;
+    }
+    std::ifstream f(cfg->model_file, std::ios::binary);
+    blob.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+  }
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, SNB_ERR_CUDA, "snb_create: no CUDA device (this library has no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, SNB_ERR_INVALID, "snb_create: bad device ordinal");
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, cfg->device);
+  if (prop.major != 10) {
+    snprintf(g_err, sizeof(g_err), "snb_create: device %d is sm_%d%d; this build carries sm_100a code only", cfg->device, prop.major, prop.minor);
+    return SNB_ERR_CUDA;
+  }
+
+  snb_ctx* c = new snb_ctx();
+  c->cfg = *cfg;
+  if (cfg->model_file) c->model_file = cfg->model_file;
+  c->cfg.model_file = nullptr; c->cfg.weights = nullptr;
+  c->H = cfg->height; c->W = cfg->width; c->K = cfg->K; c->D = cfg->D; c->maxB = cfg->max_batch;
+  const int s = 1 << c->K;
+  c->Hp = (c->H + s - 1) / s * s; c->Wp = (c->W + s - 1) / s * s;
+  c->h = c->Hp / s; c->w = c->Wp / s;
+  c->qmul = (float)((double)(s * c->D) / (192.0 * 2.60443857769133e-06));
+  c->in_bytes = (size_t)6 * c->H * c->W;
+  c->out_bytes = (size_t)4 * c->H * c->W;
+  c->frame_bytes = (size_t)c->H * 3 / 2 * 2 * c->W;
+
+  auto bail = [&](int code) { snprintf(g_err, sizeof(g_err), "%s", c->err); free_ctx(c); delete c; return code; };
+  if (cudaSetDevice(cfg->device) != cudaSuccess) { snprintf(c->err, sizeof(c->err), "cudaSetDevice failed"); return bail(SNB_ERR_CUDA); }
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { snprintf(c->err, sizeof(c->err), "stream create failed"); return bail(SNB_ERR_CUDA); }
+  for (auto& e : c->ev) cudaEventCreate(&e);
+  int r = parse_blob(c, blob.data(), blob.size());
+  if (r != SNB_OK) return bail(r);
+  r = upload_weights(c);
+  if (r != SNB_OK) return bail(r);
+  if (cudaMalloc(&c->d_in, c->in_bytes * c->maxB) != cudaSuccess || cudaMalloc(&c->d_out, c->out_bytes * c->maxB) != cudaSuccess ||
+      cudaMalloc(&c->d_frames, c->frame_bytes * c->maxB) != cudaSuccess) {
+    snprintf(c->err, sizeof(c->err), "cudaMalloc io staging failed");
+    return bail(SNB_ERR_NOMEM);
+  }
+  r = build_plan(c);
+  if (r != SNB_OK) return bail(r);
+  // one eager warm-up pass: sets kernel attributes outside graph capture and surfaces launch errors now
+  cudaMemsetAsync(c->d_in, 0, c->in_bytes * c->maxB, c->stream);
+  launch_pre_s8(c->d_in, c->img, c->maxB, c->H, c->W, c->stream);
+  r = run_plan(c, c->maxB, c->stream, false);
+  if (r == SNB_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) {
+    snprintf(c->err, sizeof(c->err), "warm-up pass failed: %s", cudaGetErrorString(cudaGetLastError()));
+    r = SNB_ERR_CUDA;
+  }
+  if (r != SNB_OK) return bail(r);
+  c->fps_t0 = now_s();
+  c->worker = std::thread(worker_main, c);
+  *out = c;
+  return SNB_OK;
+}
+
+void snb_destroy(snb_ctx* c) {
+  if (!c) return;
+  {
+    std::unique_lock<std::mutex> lk(c->mu);
+    c->stop = true;
+  }
+  c->cv_push.notify_all(); c->cv_pop.notify_all();
+  if (c->worker.joinable()) c->worker.join();
+  cudaSetDevice(c->cfg.device);
+  cudaDeviceSynchronize();
+  free_ctx(c);
+  delete c;
+}
+
+int snb_set_weights(snb_ctx* c, const void* blob, uint64_t bytes, int is_device) {
+  if (!c || !blob || !bytes) return fail(c, SNB_ERR_INVALID, "snb_set_weights: bad arguments");
+  std::lock_guard<std::mutex> run(c->run_mu);
+  cudaSetDevice(c->cfg.device);
+  cudaStreamSynchronize(c->stream);
+  std::vector<char> host;
+  if (is_device) {
+    host.resize(bytes);
+    CK(c, cudaMemcpy(host.data(), blob, bytes, cudaMemcpyDeviceToHost));
+    blob = host.data();
+  }
+  int r = parse_blob(c, blob, bytes);
+  if (r != SNB_OK) return r;
+  // device pointers baked into the plan/graphs change: rebuild both
+  for (auto& g : c->graphs) cudaGraphExecDestroy(g.second);
+  c->graphs.clear();
+  r = upload_weights(c);
+  if (r != SNB_OK) return r;
+  return build_plan(c);
+}
+
+int snb_get_io(const snb_ctx* c, snb_tensor_props* in, snb_tensor_props* out) {
+  if (!c) return SNB_ERR_INVALID;
+  if (in) {
+    memset(in, 0, sizeof(*in));
+    const int32_t s[4] = {1, 6, c->H, c->W};
+    memcpy(in->valid_shape, s, sizeof(s)); memcpy(in->aligned_shape, s, sizeof(s));
+    in->tensor_layout = SNB_LAYOUT_NCHW; in->tensor_type = SNB_TENSOR_S8;
+    in->scale_len = 1; in->scale = 1.0f / 128.0f; in->mem_size = c->in_bytes;
+  }
+  if (out) {
+    memset(out, 0, sizeof(*out));
+    const int32_t s[4] = {1, 1, c->H, c->W};
+    memcpy(out->valid_shape, s, sizeof(s)); memcpy(out->aligned_shape, s, sizeof(s));
+    out->tensor_layout = SNB_LAYOUT_NCHW; out->tensor_type = SNB_TENSOR_S32;
+    out->scale_len = 1; out->scale = 2.60443857769133e-06f; out->mem_size = c->out_bytes;
+  }
+  return SNB_OK;
+}
+
+int snb_get_model_input_size(const snb_ctx* c, int32_t idx, int32_t* w, int32_t* h) {
+  if (!c || idx != 0 || !w || !h) return SNB_ERR_INVALID;
+  *w = c->W; *h = c->H;
+  return SNB_OK;
+}
+
+// one chunk (<= maxB pairs) on stream st; inputs already in c->d_in / c->img as selected by `src`
+static int run_chunk(snb_ctx* c, int B, const int8_t* d_in, const uint8_t* d_frames, int32_t* d_out, cudaStream_t st) {
+  cudaError_t e;
+  if (d_frames)
+    e = launch_pre_nv12(d_frames, c->img, nullptr, B, c->H, c->W, (c->cfg.flags & SNB_FLAG_CORRECT_CHROMA) ? 1 : 0, st);
+  else
+    e = launch_pre_s8(d_in, c->img, B, c->H, c->W, st);
+  if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "pre: %s", cudaGetErrorString(e)); return SNB_ERR_CUDA; }
+  int r = run_plan(c, B, st, !(c->cfg.flags & (SNB_FLAG_NO_GRAPH | SNB_FLAG_KEEP_STAGES)));
+  if (r != SNB_OK) return r;
+  Plane d = c->disp_final; d.n = B;
+  e = launch_post_quant(d, d_out, c->H, c->W, c->qmul, st);
+  if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "post: %s", cudaGetErrorString(e)); return SNB_ERR_CUDA; }
+  c->last_B = B;
+  return SNB_OK;
+}
+
+static int infer_host(snb_ctx* c, const int8_t* in, const uint8_t* frames, int32_t* out, int batch) {
+  if (!c || (!in && !frames) || !out || batch < 1) return fail(c, SNB_ERR_INVALID, "snb_infer: bad arguments");
+  std::lock_guard<std::mutex> run(c->run_mu);
+  CK(c, cudaSetDevice(c->cfg.device));
+  const double t0 = now_s();
+  cudaStream_t st = c->stream;
+  float gpu_ms = 0.f;
+  for (int b0 = 0; b0 < batch; b0 += c->maxB) {
+    const int B = std::min(c->maxB, batch - b0);
+    if (frames) CK(c, cudaMemcpyAsync(c->d_frames, frames + (size_t)b0 * c->frame_bytes, c->frame_bytes * B, cudaMemcpyHostToDevice, st));
+    else CK(c, cudaMemcpyAsync(c->d_in, in + (size_t)b0 * c->in_bytes, c->in_bytes * B, cudaMemcpyHostToDevice, st));
+    cudaEventRecord(c->ev[0], st);
+    int r = run_chunk(c, B, c->d_in, frames ? c->d_frames : nullptr, c->d_out, st);
+    if (r != SNB_OK) { snprintf(g_err, sizeof(g_err), "%s", c->err); return r; }
+    cudaEventRecord(c->ev[1], st);
+    CK(c, cudaMemcpyAsync(out + (size_t)b0 * c->H * c->W, c->d_out, c->out_bytes * B, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    float ms = 0.f; cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); gpu_ms += ms;
+  }
+  const double t1 = now_s();
+  c->stat.gpu_ms = gpu_ms;
+  c->stat.infer_time_ms = (int)((t1 - t0) * 1e3 + 0.5);
+  c->stat.kernel_launches = (int)c->ops.size() + 2;
+  c->fps_in += batch; c->fps_out += batch;
+  c->stat.fps_updated = 0;
+  if (t1 - c->fps_t0 >= 1.0) {     // dnn_node refreshes its fps statistics about once a second
+    c->stat.input_fps = (float)(c->fps_in / (t1 - c->fps_t0));
+    c->stat.output_fps = (float)(c->fps_out / (t1 - c->fps_t0));
+    c->fps_in = c->fps_out = 0; c->fps_t0 = t1; c->stat.fps_updated = 1;
+  }
+  return SNB_OK;
+}
+
+int snb_infer(snb_ctx* c, const int8_t* in, int32_t* out, int32_t batch) { return infer_host(c, in, nullptr, out, batch); }
+
+int snb_infer_nv12(snb_ctx* c, const uint8_t* frames, int32_t* out, int32_t batch) { return infer_host(c, nullptr, frames, out, batch); }
+
+int snb_infer_device(snb_ctx* c, const int8_t* d_in, int32_t* d_out, int32_t batch, void* cuda_stream) {
+  if (!c || !d_in || !d_out || batch < 1) return fail(c, SNB_ERR_INVALID, "snb_infer_device: bad arguments");
+  std::lock_guard<std::mutex> run(c->run_mu);
+  CK(c, cudaSetDevice(c->cfg.device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+  for (int b0 = 0; b0 < batch; b0 += c->maxB) {
+    const int B = std::min(c->maxB, batch - b0);
+    int r = run_chunk(c, B, d_in + (size_t)b0 * c->in_bytes, nullptr, d_out + (size_t)b0 * c->H * c->W, st);
+    if (r != SNB_OK) { snprintf(g_err, sizeof(g_err), "%s", c->err); return r; }
+  }
+  if (!cuda_stream) CK(c, cudaStreamSynchronize(st));
+  return SNB_OK;
+}
+
+int snb_infer_async(snb_ctx* c, const int8_t* in, int32_t* out, int32_t batch, snb_done_fn done, void* user, int32_t timeout_ms) {
+  if (!c || !in || !out || batch < 1) return fail(c, SNB_ERR_INVALID, "snb_infer_async: bad arguments");
+  std::unique_lock<std::mutex> lk(c->mu);
+  const int cap = std::max(1, c->cfg.task_num);
+  auto room = [&] { return c->stop || c->inflight < cap; };
+  if (timeout_ms < 0) c->cv_push.wait(lk, room);
+  else if (!c->cv_push.wait_for(lk, std::chrono::milliseconds(timeout_ms), room)) return fail(c, SNB_ERR_BUSY, "snb_infer_async: no free task slot");
+  if (c->stop) return SNB_ERR_INVALID;
+  c->queue.push_back(Task{in, out, batch, done, user});
+  ++c->inflight;
+  lk.unlock();
+  c->cv_pop.notify_one();
+  return SNB_OK;
+}
+
+int snb_wait_all(snb_ctx* c) {
+  if (!c) return SNB_ERR_INVALID;
+  std::unique_lock<std::mutex> lk(c->mu);
+  c->cv_push.wait(lk, [&] { return c->inflight == 0 || c->stop; });
+  return SNB_OK;
+}
+
+int snb_get_rt_stat(const snb_ctx* c, snb_rt_stat* s) {
+  if (!c || !s) return SNB_ERR_INVALID;
+  *s = c->stat;
+  return SNB_OK;
+}
+
+int64_t snb_debug_read(snb_ctx* c, const char* name, float* dst, uint64_t cap, int32_t shape[5]) {
+  if (!c || !name) return SNB_ERR_INVALID;
+  if (!(c->cfg.flags & SNB_FLAG_KEEP_STAGES)) return fail(c, SNB_ERR_INVALID, "snb_debug_read needs SNB_FLAG_KEEP_STAGES");
+  auto it = c->stages.find(name);
+  if (it == c->stages.end()) return fail(c, SNB_ERR_INVALID, "snb_debug_read: unknown stage");
+  std::lock_guard<std::mutex> run(c->run_mu);
+  cudaSetDevice(c->cfg.device);
+  cudaStreamSynchronize(c->stream);
+  const Stage& s = it->second;
+  const int B = std::max(1, c->last_B);
+  if (s.is_plane) {
+    const Plane& p = s.p;
+    const size_t n = (size_t)B * p.d * p.h * p.w;
+    if (shape) { shape[0] = B; shape[1] = 1; shape[2] = p.d; shape[3] = p.h; shape[4] = p.w; }
+    if (!dst) return (int64_t)n;
+    if (cap < n) return SNB_ERR_INVALID;
+    CK(c, cudaMemcpy(dst, p.p, n * 4, cudaMemcpyDeviceToHost));
+    return (int64_t)n;
+  }
+  const Tens& t = s.t;
+  const int N = s.nmul * B;
+  const size_t n = (size_t)N * t.c * t.d * t.h * t.w;
+  if (shape) { shape[0] = N; shape[1] = t.c; shape[2] = t.d; shape[3] = t.h; shape[4] = t.w; }
+  if (!dst) return (int64_t)n;
+  if (cap < n) return SNB_ERR_INVALID;
+  std::vector<float> tmp((size_t)N * t.cb * t.d * t.h * t.w * 8);
+  CK(c, cudaMemcpy(tmp.data(), t.p, tmp.size() * 4, cudaMemcpyDeviceToHost));
+  const size_t sp = (size_t)t.d * t.h * t.w;
+  for (int nn = 0; nn < N; ++nn)
+    for (int ch = 0; ch < t.c; ++ch) {
+      const float* src = tmp.data() + (((size_t)nn * t.cb + ch / 8) * sp) * 8 + ch % 8;
+      float* d = dst + ((size_t)nn * t.c + ch) * sp;
+      for (size_t i = 0; i < sp; ++i) d[i] = src[i * 8];
+    }
+  return (int64_t)n;
+}
+
+int snb_profile_pass(snb_ctx* c, int32_t batch, snb_kernel_time* out, int32_t cap) {
+  if (!c || batch < 1 || batch > c->maxB) return fail(c, SNB_ERR_INVALID, "snb_profile_pass: bad batch");
+  std::lock_guard<std::mutex> run(c->run_mu);
+  CK(c, cudaSetDevice(c->cfg.device));
+  cudaStream_t st = c->stream;
+  const int n = (int)c->ops.size() + 2;
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) cudaEventCreate(&e);
+  cudaEventRecord(ev[0], st);
+  launch_pre_s8(c->d_in, c->img, batch, c->H, c->W, st);
+  cudaEventRecord(ev[1], st);
+  for (int i = 0; i < (int)c->ops.size(); ++i) {
+    cudaError_t e = c->ops[i].fn(batch, st);
+    if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "%s: %s", c->ops[i].name.c_str(), cudaGetErrorString(e)); return SNB_ERR_CUDA; }
+    cudaEventRecord(ev[i + 2], st);
+  }
+  Plane d = c->disp_final; d.n = batch;
+  launch_post_quant(d, c->d_out, c->H, c->W, c->qmul, st);
+  cudaEventRecord(ev[n], st);
+  CK(c, cudaStreamSynchronize(st));
+  for (int i = 0; i < n && i < cap; ++i) {
+    memset(&out[i], 0, sizeof(out[i]));
+    const char* nm = i == 0 ? "pre_s8" : (i == n - 1 ? "post_quant" : c->ops[i - 1].name.c_str());
+    snprintf(out[i].name, sizeof(out[i].name), "%s", nm);
+    cudaEventElapsedTime(&out[i].ms, ev[i], ev[i + 1]);
+    if (i > 0 && i < n - 1) { out[i].flops = c->ops[i - 1].flops * batch; out[i].bytes = c->ops[i - 1].bytes * batch; }
+    else if (i == 0) out[i].bytes = (double)batch * (c->in_bytes + 2.0 * c->Hp * c->Wp * 32);
+    else out[i].bytes = (double)batch * (4.0 * c->Hp * c->Wp + c->out_bytes);
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return n;
+}
+
+}  // extern "C"
+
+static void worker_main(snb_ctx* c) {
+  for (;;) {
+    Task t;
+    {
+      std::unique_lock<std::mutex> lk(c->mu);
+      c->cv_pop.wait(lk, [&] { return c->stop || !c->queue.empty(); });
+      if (c->queue.empty()) return;           // stop requested and drained
+      t = c->queue.front();
+      c->queue.pop_front();
+    }
+    int r = infer_host(c, t.in, nullptr, t.out, t.batch);
+    snb_rt_stat st = c->stat;
+    if (t.done) t.done(t.user, r, &st);
+    {
+      std::unique_lock<std::mutex> lk(c->mu);
+      --c->inflight;
+    }
+    c->cv_push.notify_all();
+  }
+}

@@ -1,0 +1,235 @@
+// HBM-bound kernels of the StereoNet path: input conversion (P1-P3), cost-volume build (M2),
+// soft-argmin (M4), refinement glue (M5) and output quantisation (O1).  All coalesced along x,
+// 128-bit accesses where the layout allows, shared-memory staging where data is reused across D.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace snb {
+
+// ------------------------------------------------------------------------------------------------
+// s8 NCHW [B,6,H,W] -> C8 image [2B][1][Hp][Wp][8].  Restates the tensor semantics the BPU model
+// gives its input: value = s8 * (1/128) (preprocess.cpp:1037), channels 0-2 left, 3-5 right.
+__global__ void k_pre_s8(const int8_t* __restrict__ s8, float* __restrict__ img, int B, int H, int W,
+                         int Hp, int Wp) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int n = blockIdx.z;                  // 0..2B-1
+  if (x >= Wp) return;
+  const int b = n % B, view = n / B;
+  float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (x < W && y < H) {
+    const int8_t* src = s8 + (((size_t)b * 6 + view * 3) * H + y) * W + x;
+    const size_t plane = (size_t)H * W;
+    v0.x = (float)src[0] * 0.0078125f;
+    v0.y = (float)src[plane] * 0.0078125f;
+    v0.z = (float)src[2 * plane] * 0.0078125f;
+  }
+  float4* dst = reinterpret_cast<float4*>(img + (((size_t)n * Hp + y) * Wp + x) * 8);
+  dst[0] = v0;
+  dst[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+cudaError_t launch_pre_s8(const int8_t* s8, Tens img, int B, int H, int W, cudaStream_t st) {
+  k_pre_s8<<<dim3(cdiv(img.w, 128), img.h, 2 * B), 128, 0, st>>>(s8, img.p, B, H, W, img.h, img.w);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Side-by-side NV12 frame -> the same C8 image (and optionally the s8 tensor the reference builds).
+// Restates stereonet_node.cpp:702-738 (L/R split), preprocess.h:128-155 (YUV420TOYUV444 incl. the
+// I420-indexing quirk on NV12 data) and preprocess.cpp:1032-1040 (x-128) in one pass.
+__global__ void k_pre_nv12(const uint8_t* __restrict__ frames, float* __restrict__ img,
+                           int8_t* __restrict__ s8, int B, int H, int W, int Hp, int Wp, int correct) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int n = blockIdx.z;
+  if (x >= Wp) return;
+  const int b = n % B, view = n / B;
+  float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (x < W && y < H) {
+    const uint8_t* f = frames + (size_t)b * (H * 3 / 2) * (2 * W) + view * W;   // this view's column window
+    const int pitch = 2 * W;
+    const uint8_t yy = f[(size_t)y * pitch + x];
+    uint8_t u, v;
+    if (correct) {
+      const uint8_t* row = f + (size_t)(H + (y >> 1)) * pitch;
+      u = row[(x >> 1) * 2];
+      v = row[(x >> 1) * 2 + 1];
+    } else {
+      // the view's chroma block is [H/2][W] bytes; the reference reads it as two [H/2][W/2] planes
+      const int k = (y >> 1) * (W >> 1) + (x >> 1);
+      const int kv = k + (W * H) / 4;
+      u = f[(size_t)(H + k / W) * pitch + k % W];
+      v = f[(size_t)(H + kv / W) * pitch + kv % W];
+    }
+    const int8_t sy = (int8_t)(yy ^ 0x80), su = (int8_t)(u ^ 0x80), sv = (int8_t)(v ^ 0x80);
+    v0.x = (float)sy * 0.0078125f;
+    v0.y = (float)su * 0.0078125f;
+    v0.z = (float)sv * 0.0078125f;
+    if (s8) {
+      int8_t* d = s8 + (((size_t)b * 6 + view * 3) * H + y) * W + x;
+      const size_t plane = (size_t)H * W;
+      d[0] = sy; d[plane] = su; d[2 * plane] = sv;
+    }
+  }
+  float4* dst = reinterpret_cast<float4*>(img + (((size_t)n * Hp + y) * Wp + x) * 8);
+  dst[0] = v0;
+  dst[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+cudaError_t launch_pre_nv12(const uint8_t* frames, Tens img, int8_t* s8, int B, int H, int W, int correct,
+                            cudaStream_t st) {
+  k_pre_nv12<<<dim3(cdiv(img.w, 128), img.h, 2 * B), 128, 0, st>>>(frames, img.p, s8, B, H, W, img.h, img.w, correct);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// M2 cost-volume build.  One CTA per (row y, pair b, output block q of the gwc half): stages the
+// 64 left and 64 right gwc channels of that row in shared memory once, then emits all D hypotheses.
+//   vol block 0,1 : left concat feature (16 ch), zero where x < d
+//   vol block 2,3 : right concat feature shifted right by d, zero where x < d
+//   vol block 4..7: group-wise correlation, group = one C8 block of the 256-ch feature:
+//                   mean_8( L[g][x][:] * R[g][x-d][:] ), zero where x < d
+// Thread (x, j): consecutive threads write consecutive floats of [x][j] -> fully coalesced stores.
+__global__ void __launch_bounds__(256) k_costvol(const float* __restrict__ gwc, const float* __restrict__ cat,
+                                                 float* __restrict__ vol, int B, int D, int h, int w) {
+  extern __shared__ float sm[];
+  const int y = blockIdx.x, b = blockIdx.y, q = blockIdx.z;    // q in 0..3
+  const int pitch = w * 8 + 4;                                  // +4 floats: 8 blocks hit 8 distinct 16B lanes
+  float* sL = sm;                  // [8][pitch]
+  float* sR = sm + 8 * pitch;
+  const size_t row = (size_t)w * 8;
+  for (int i = threadIdx.x; i < 8 * w * 2; i += blockDim.x) {
+    const int j = i / (w * 2), r = i % (w * 2);                 // r: float4 index inside the row of block j
+    const size_t gl = ((((size_t)b * 32 + q * 8 + j) * h + y) * row);
+    const size_t gr = ((((size_t)(B + b) * 32 + q * 8 + j) * h + y) * row);
+    reinterpret_cast<float4*>(sL + j * pitch)[r] = __ldg(reinterpret_cast<const float4*>(gwc + gl) + r);
+    reinterpret_cast<float4*>(sR + j * pitch)[r] = __ldg(reinterpret_cast<const float4*>(gwc + gr) + r);
+  }
+  __syncthreads();
+
+  const size_t vslice = (size_t)h * w * 8;                      // one (cb, d) slice
+  float* vg = vol + ((size_t)b * 8 + 4 + q) * D * vslice + (size_t)y * row;   // gwc block 4+q
+  float* vc = vol + ((size_t)b * 8 + q) * D * vslice + (size_t)y * row;       // concat block q
+  const float* csrc = cat + ((((size_t)((q >> 1) ? B + b : b)) * 2 + (q & 1)) * h + y) * row;
+  const bool shifted = (q >> 1) != 0;
+
+  for (int e = threadIdx.x; e < w * 8; e += blockDim.x) {
+    const int x = e >> 3, j = e & 7;
+    const float4 l0 = *reinterpret_cast<const float4*>(sL + j * pitch + x * 8);
+    const float4 l1 = *reinterpret_cast<const float4*>(sL + j * pitch + x * 8 + 4);
+    const float cl = __ldg(csrc + e);                           // unshifted concat value (left blocks)
+    for (int d = 0; d < D; ++d) {
+      float g = 0.f, c = 0.f;
+      if (x >= d) {
+        const float4 r0 = *reinterpret_cast<const float4*>(sR + j * pitch + (x - d) * 8);
+        const float4 r1 = *reinterpret_cast<const float4*>(sR + j * pitch + (x - d) * 8 + 4);
+        g = l0.x * r0.x;
+        g = fmaf(l0.y, r0.y, g); g = fmaf(l0.z, r0.z, g); g = fmaf(l0.w, r0.w, g);
+        g = fmaf(l1.x, r1.x, g); g = fmaf(l1.y, r1.y, g); g = fmaf(l1.z, r1.z, g); g = fmaf(l1.w, r1.w, g);
+        g *= 0.125f;
+        c = shifted ? __ldg(csrc + e - d * 8) : cl;
+      }
+      vg[(size_t)d * vslice + e] = g;
+      vc[(size_t)d * vslice + e] = c;
+    }
+  }
+}
+
+cudaError_t launch_costvol(Tens gwc, Tens cat, Tens vol, int B, int D, cudaStream_t st) {
+  const int h = gwc.h, w = gwc.w;
+  const size_t smem = (size_t)2 * 8 * (w * 8 + 4) * sizeof(float);
+  if (need_attr(2)) cudaFuncSetAttribute(k_costvol, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  k_costvol<<<dim3(h, B, 4), 256, smem, st>>>(gwc.p, cat.p, vol.p, B, D, h, w);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// M4 softmax over D + soft-argmin, online (single pass over the cost column), fp32 throughout.
+__global__ void k_softargmin(const float* __restrict__ cost, float* __restrict__ disp, int D, int hw, float invD) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (i >= hw) return;
+  const float* c = cost + (size_t)b * D * hw + i;
+  float m = -INFINITY, s = 0.f, t = 0.f;
+  for (int d = 0; d < D; ++d) {
+    const float v = __ldg(c + (size_t)d * hw);
+    if (v > m) {
+      const float r = expf(m - v);
+      s *= r; t *= r; m = v;
+    }
+    const float e = expf(v - m);
+    s += e;
+    t = fmaf(e, (float)d, t);
+  }
+  disp[(size_t)b * hw + i] = t / s * invD;
+}
+
+cudaError_t launch_softargmin(Plane cost, Plane disp, cudaStream_t st) {
+  const int hw = cost.h * cost.w;
+  k_softargmin<<<dim3(cdiv(hw, 128), cost.n), 128, 0, st>>>(cost.p, disp.p, cost.d, hw, 1.0f / cost.d);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// M5 glue: channel 0 = x2 bilinear upsample of the disparity (align_corners=False), channels 1-3 =
+// left image bilinearly resized to the stage resolution (integer factor f: mean of the central 2x2).
+__global__ void k_refine_in(const float* __restrict__ disp, const float* __restrict__ img, float* __restrict__ out,
+                            int h, int w, int Hf, int Wf, int f) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, b = blockIdx.z;
+  const int H2 = 2 * h, W2 = 2 * w;
+  if (x >= W2) return;
+  // PyTorch upsample_bilinear2d, scale 0.5: src = max((dst+0.5)*0.5-0.5, 0)
+  const float sy = fmaxf((y + 0.5f) * 0.5f - 0.5f, 0.f), sx = fmaxf((x + 0.5f) * 0.5f - 0.5f, 0.f);
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+  const float ly1 = sy - y0, lx1 = sx - x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+  const float* dp = disp + (size_t)b * h * w;
+  const float up = ly0 * (lx0 * __ldg(dp + y0 * w + x0) + lx1 * __ldg(dp + y0 * w + x1)) +
+                   ly1 * (lx0 * __ldg(dp + y1 * w + x0) + lx1 * __ldg(dp + y1 * w + x1));
+  float4 o;
+  o.x = up;
+  const float* ip = img + (size_t)b * Hf * Wf * 8;
+  if (f == 1) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(ip + ((size_t)y * Wf + x) * 8));
+    o.y = v.x; o.z = v.y; o.w = v.z;
+  } else {
+    const int yy = y * f + f / 2 - 1, xx = x * f + f / 2 - 1;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(ip + ((size_t)yy * Wf + xx) * 8));
+    const float4 bq = __ldg(reinterpret_cast<const float4*>(ip + ((size_t)yy * Wf + xx + 1) * 8));
+    const float4 c = __ldg(reinterpret_cast<const float4*>(ip + ((size_t)(yy + 1) * Wf + xx) * 8));
+    const float4 d = __ldg(reinterpret_cast<const float4*>(ip + ((size_t)(yy + 1) * Wf + xx + 1) * 8));
+    o.y = 0.5f * (0.5f * a.x + 0.5f * bq.x) + 0.5f * (0.5f * c.x + 0.5f * d.x);
+    o.z = 0.5f * (0.5f * a.y + 0.5f * bq.y) + 0.5f * (0.5f * c.y + 0.5f * d.y);
+    o.w = 0.5f * (0.5f * a.z + 0.5f * bq.z) + 0.5f * (0.5f * c.z + 0.5f * d.z);
+  }
+  float4* dst = reinterpret_cast<float4*>(out + (((size_t)b * H2 + y) * W2 + x) * 8);
+  dst[0] = o;
+  dst[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+cudaError_t launch_refine_in(Plane disp, Tens img_full, Tens out, int B, cudaStream_t st) {
+  const int f = img_full.h / out.h;
+  k_refine_in<<<dim3(cdiv(out.w, 128), out.h, B), 128, 0, st>>>(disp.p, img_full.p, out.p, disp.h, disp.w,
+                                                               img_full.h, img_full.w, f);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Output tensor as the reference reads it (stereonet_node.cpp:1033): s32 NCHW [B,1,H,W], cropped
+// from the padded map; q = rint(dn * qmul) so that q * 2.60443857769133e-06 * 192 = pixels.
+__global__ void k_post_quant(const float* __restrict__ disp, int32_t* __restrict__ out, int H, int W, int Hp, int Wp,
+                             float qmul) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, b = blockIdx.z;
+  if (x >= W) return;
+  out[((size_t)b * H + y) * W + x] = __float2int_rn(disp[((size_t)b * Hp + y) * Wp + x] * qmul);
+}
+
+cudaError_t launch_post_quant(Plane disp, int32_t* out, int H, int W, float qmul, cudaStream_t st) {
+  k_post_quant<<<dim3(cdiv(W, 128), H, disp.n), 128, 0, st>>>(disp.p, out, H, W, disp.h, disp.w, qmul);
+  return cudaGetLastError();
+}
+
+}  // namespace snb

@@ -1,0 +1,26 @@
+// Launchers of the sm_100a kernels (one per SURVEY.md §8a row / Appendix A entry).
+#pragma once
+#include "common.cuh"
+
+namespace snb {
+
+// k_conv_direct.cu — fp32 CUDA-core convolutions (M1, M3, M5)
+cudaError_t launch_conv_direct(ConvParams p, int cout, cudaStream_t st);
+cudaError_t launch_conv_to1(const ConvTo1Params& p, cudaStream_t st);
+
+// k_mem.cu — HBM-bound kernels
+// P3 tail on device: s8 NCHW [B,6,H,W] -> C8 [2B][1][Hp][Wp][8] (x/128; left n<B, right n>=B; ch 3..7 = 0)
+cudaError_t launch_pre_s8(const int8_t* s8, Tens img, int B, int H, int W, cudaStream_t st);
+// P1-P3 on device: side-by-side NV12 frames [B][H*3/2][2W] -> same C8 image tensor, and optionally the s8 tensor
+cudaError_t launch_pre_nv12(const uint8_t* frames, Tens img, int8_t* s8_or_null, int B, int H, int W,
+                            int correct_chroma, cudaStream_t st);
+// M2: gwc [2B][32][h][w][8], cat [2B][2][h][w][8] -> vol [B][8][D][h][w][8]
+cudaError_t launch_costvol(Tens gwc, Tens cat, Tens vol, int B, int D, cudaStream_t st);
+// M4: cost [B][D][h][w] -> disp [B][h][w] = sum_d softmax(cost)_d * d / D
+cudaError_t launch_softargmin(Plane cost, Plane disp, cudaStream_t st);
+// M5 glue: x2 bilinear(disp) ++ left image resized to (2h,2w) -> C8 [B][1][2h][2w][8] (ch 4..7 = 0)
+cudaError_t launch_refine_in(Plane disp, Tens img_full, Tens out, int B, cudaStream_t st);
+// O1 head: normalised disparity [B][Hp][Wp] -> s32 NCHW [B,1,H,W] (crop), q = rint(dn * qmul)
+cudaError_t launch_post_quant(Plane disp, int32_t* out, int H, int W, float qmul, cudaStream_t st);
+
+}  // namespace snb

@@ -1,0 +1,378 @@
+// Weight loading, scratch arena and the static op plan of the StereoNet forward pass.
+// Topology: SURVEY.md §2.3 (reconstructed from the reference's .hbm tensor table); the free
+// choices are documented in DESIGN.md §2 and restated identically in oracle/stereonet_ref.py.
+#include "net.h"
+
+#include <string.h>
+
+#include <algorithm>
+
+#include "kernels.cuh"
+
+namespace snb {
+
+static const int LAYER_BLOCKS[4] = {3, 16, 3, 3};
+static const int LAYER_CH[4] = {32, 64, 128, 128};
+static const int REF_DIL[6] = {1, 2, 4, 8, 1, 1};
+
+// ---- weight blob ("SNB2WGT1", oracle/weights.py documents the layout) -----------------------------
+int parse_blob(snb_ctx* c, const void* blob, size_t bytes) {
+  const uint8_t* p = static_cast<const uint8_t*>(blob);
+  if (bytes < 24 || memcmp(p, "SNB2WGT1", 8) != 0) {
+    snprintf(c->err, sizeof(c->err), "model_file is not a SNB2WGT1 weight blob");
+    return SNB_ERR_MODEL;
+  }
+  uint32_t ver, K, n;
+  memcpy(&ver, p + 8, 4); memcpy(&K, p + 12, 4); memcpy(&n, p + 16, 4);
+  if (ver != 1 || bytes < 24 + (size_t)n * 104) {
+    snprintf(c->err, sizeof(c->err), "weight blob: bad version or truncated table");
+    return SNB_ERR_MODEL;
+  }
+  const size_t base = (24 + (size_t)n * 104 + 63) / 64 * 64;
+  c->wts.clear();
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint8_t* e = p + 24 + (size_t)i * 104;
+    char name[65]; memcpy(name, e, 64); name[64] = 0;
+    uint32_t ndim, dims[5]; uint64_t off, nb;
+    memcpy(&ndim, e + 64, 4); memcpy(dims, e + 68, 20); memcpy(&off, e + 88, 8); memcpy(&nb, e + 96, 8);
+    if (ndim > 5 || base + off + nb > bytes) {
+      snprintf(c->err, sizeof(c->err), "weight blob: tensor %s out of range", name);
+      return SNB_ERR_MODEL;
+    }
+    HostTensor t;
+    for (uint32_t k = 0; k < ndim; ++k) t.shape.push_back((int)dims[k]);
+    t.data.resize(nb / 4);
+    memcpy(t.data.data(), p + base + off, nb);
+    c->wts[name] = std::move(t);
+  }
+  c->blob_K = (int)K;
+  return SNB_OK;
+}
+
+static int pack_conv(snb_ctx* c, const std::string& name) {
+  auto wi = c->wts.find(name + ".weight"), bi = c->wts.find(name + ".bias");
+  if (wi == c->wts.end() || bi == c->wts.end()) {
+    snprintf(c->err, sizeof(c->err), "weight blob lacks %s", name.c_str());
+    return SNB_ERR_MODEL;
+  }
+  const HostTensor& W = wi->second;
+  ConvW cw;
+  cw.cout = W.shape[0]; cw.cin = W.shape[1];
+  const bool is3d = W.shape.size() == 5;
+  cw.kz = is3d ? W.shape[2] : 1;
+  cw.ks = W.shape.back();
+  const int ntap = cw.ks * cw.ks, cbin = (cw.cin + 7) / 8;
+  std::vector<float> packed;
+  if (cw.cout == 1) {
+    packed.assign((size_t)cbin * cw.kz * 9 * 8, 0.f);
+    for (int ci = 0; ci < cw.cin; ++ci)
+      for (int kz = 0; kz < cw.kz; ++kz)
+        for (int t = 0; t < ntap; ++t)
+          packed[(((size_t)(ci / 8) * cw.kz + kz) * 9 + t) * 8 + ci % 8] =
+              W.data[(((size_t)ci) * cw.kz + kz) * ntap + t];
+    cw.b0 = bi->second.data[0];
+  } else {
+    const int CO = (cw.cout % 32 == 0) ? 32 : 16;
+    const int ncc = cw.cout / CO;
+    packed.assign((size_t)ncc * cbin * cw.kz * ntap * 8 * CO, 0.f);
+    for (int co = 0; co < cw.cout; ++co)
+      for (int ci = 0; ci < cw.cin; ++ci)
+        for (int kz = 0; kz < cw.kz; ++kz)
+          for (int t = 0; t < ntap; ++t) {
+            const size_t dst = (((((size_t)(co / CO) * cbin + ci / 8) * cw.kz + kz) * ntap + t) * 8 + ci % 8) * CO + co % CO;
+            packed[dst] = W.data[((((size_t)co * cw.cin + ci) * cw.kz + kz) * ntap) + t];
+          }
+  }
+  if (cudaMalloc(&cw.w, packed.size() * 4) != cudaSuccess || cudaMalloc(&cw.b, cw.cout * 4) != cudaSuccess) {
+    snprintf(c->err, sizeof(c->err), "cudaMalloc weights failed");
+    return SNB_ERR_NOMEM;
+  }
+  c->wallocs.push_back(cw.w); c->wallocs.push_back(cw.b);
+  cudaMemcpy(cw.w, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(cw.b, bi->second.data.data(), cw.cout * 4, cudaMemcpyHostToDevice);
+  c->convs[name] = cw;
+  return SNB_OK;
+}
+
+int upload_weights(snb_ctx* c) {
+  for (void* p : c->wallocs) cudaFree(p);
+  c->wallocs.clear(); c->convs.clear();
+  if (c->blob_K != c->K) {
+    snprintf(c->err, sizeof(c->err), "weight blob was generated for K=%d, config asks K=%d", c->blob_K, c->K);
+    return SNB_ERR_MODEL;
+  }
+  std::vector<std::string> names;
+  for (auto& kv : c->wts) {
+    const std::string& n = kv.first;
+    if (n.size() > 7 && n.compare(n.size() - 7, 7, ".weight") == 0) names.push_back(n.substr(0, n.size() - 7));
+  }
+  for (auto& n : names) {
+    int r = pack_conv(c, n);
+    if (r != SNB_OK) return r;
+  }
+  if (cudaDeviceSynchronize() != cudaSuccess) return SNB_ERR_CUDA;
+  return SNB_OK;
+}
+
+// ---- scratch arena: stream-ordered reuse of activation buffers -----------------------------------
+void* Arena::get(size_t bytes) {
+  bytes = (bytes + 255) / 256 * 256;
+  if (reuse) {
+    int best = -1;
+    for (int i = 0; i < (int)blks.size(); ++i)
+      if (blks[i].free && blks[i].bytes >= bytes && (best < 0 || blks[i].bytes < blks[best].bytes)) best = i;
+    if (best >= 0 && blks[best].bytes <= bytes * 2) { blks[best].free = false; return blks[best].p; }
+  }
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+  cudaMemset(p, 0, bytes);
+  blks.push_back({p, bytes, false});
+  total += bytes;
+  return p;
+}
+void Arena::put(void* p) {
+  if (!reuse) return;
+  for (auto& b : blks) if (b.p == p) b.free = true;
+}
+void Arena::release_all() {
+  for (auto& b : blks) cudaFree(b.p);
+  blks.clear(); total = 0;
+}
+
+// ---- plan builder --------------------------------------------------------------------------------
+struct Builder {
+  snb_ctx* c;
+  int maxB;
+  bool fail = false;
+
+  Tens alloc(int nmul, int ch, int d, int h, int w) {
+    Tens t; t.n = nmul * maxB; t.c = ch; t.cb = (ch + 7) / 8; t.d = d; t.h = h; t.w = w;
+    t.p = static_cast<float*>(c->arena.get(t.bytes()));
+    if (!t.p) fail = true;
+    return t;
+  }
+  Plane palloc(int d, int h, int w) {
+    Plane p; p.n = maxB; p.d = d; p.h = h; p.w = w;
+    p.p = static_cast<float*>(c->arena.get(p.bytes()));
+    if (!p.p) fail = true;
+    return p;
+  }
+  void free(const Tens& t) { c->arena.put(t.p); }
+  void free(const Plane& p) { c->arena.put(p.p); }
+  void tap(const std::string& name, const Tens& t, int nmul) { Stage s; s.t = t; s.nmul = nmul; c->stages[name] = s; }
+  void tap(const std::string& name, const Plane& p) { Stage s; s.is_plane = true; s.p = p; c->stages[name] = s; }
+
+  // generic convolution on the fp32 direct path
+  Tens conv(const std::string& name, const Tens& in, int nmul, int stride, int dil, bool relu, const Tens* res) {
+    auto it = c->convs.find(name);
+    if (it == c->convs.end()) { fail = true; snprintf(c->err, sizeof(c->err), "no weights for %s", name.c_str()); return Tens(); }
+    const ConvW cw = it->second;
+    const int ho = (in.h + stride - 1) / stride, wo = (in.w + stride - 1) / stride;
+    Tens out = alloc(nmul, cw.cout, in.d, ho, wo);
+    ConvParams p{};
+    p.in = in.p; p.out = out.p; p.w = cw.w; p.bias = cw.b; p.res = res ? res->p : nullptr;
+    p.CBin = in.cb; p.Din = in.d; p.Hin = in.h; p.Win = in.w;
+    p.CBout = out.cb; p.Dout = out.d; p.Hout = ho; p.Wout = wo;
+    p.ks = cw.ks; p.kz = cw.kz; p.stride = stride; p.dil = dil; p.relu = relu ? 1 : 0;
+    Op op; op.name = name;
+    const int cout = cw.cout;
+    op.fn = [p, nmul, cout](int B, cudaStream_t st) mutable { ConvParams q = p; q.N = nmul * B; return launch_conv_direct(q, cout, st); };
+    const double px = (double)nmul * in.d * ho * wo;
+    op.flops = 2.0 * px * cw.cout * cw.cin * cw.ks * cw.ks * cw.kz;
+    op.bytes = 4.0 * (nmul * (double)in.d * in.h * in.w * in.cb * 8 + px * out.cb * 8 * (res ? 2 : 1));
+    c->ops.push_back(op);
+    return out;
+  }
+
+  Plane conv_to1(const std::string& name, const Tens& in, int dil, bool relu, const float* res, int res_stride) {
+    auto it = c->convs.find(name);
+    if (it == c->convs.end()) { fail = true; snprintf(c->err, sizeof(c->err), "no weights for %s", name.c_str()); return Plane(); }
+    const ConvW cw = it->second;
+    Plane out = palloc(in.d, in.h, in.w);
+    ConvTo1Params p{};
+    p.in = in.p; p.out = out.p; p.w = cw.w; p.bias = cw.b0; p.res = res; p.res_stride = res_stride;
+    p.CBin = in.cb; p.D = in.d; p.H = in.h; p.W = in.w; p.kz = cw.kz; p.dil = dil; p.relu = relu ? 1 : 0;
+    Op op; op.name = name;
+    op.fn = [p](int B, cudaStream_t st) { ConvTo1Params q = p; q.N = B; return launch_conv_to1(q, st); };
+    const double px = (double)in.d * in.h * in.w;
+    op.flops = 2.0 * px * cw.cin * 9 * cw.kz;
+    op.bytes = 4.0 * (px * in.cb * 8 + px * (res ? 2 : 1));
+    c->ops.push_back(op);
+    return out;
+  }
+};
+
+int build_plan(snb_ctx* c) {
+  c->ops.clear(); c->stages.clear();
+  c->arena.release_all();
+  c->arena.reuse = !(c->cfg.flags & SNB_FLAG_KEEP_STAGES);
+  Builder b{c, c->maxB};
+  const int K = c->K, D = c->D, Hp = c->Hp, Wp = c->Wp, h = c->h, w = c->w;
+
+  // input image, C8 [2B][1][Hp][Wp][8]; the pre-process op is issued by the caller (s8 or NV12 source)
+  c->img = b.alloc(2, 3, 1, Hp, Wp);
+  Tens img = c->img;
+  b.tap("img", img, 2);
+
+  // ---- M1 siamese backbone (left and right batched as n = 2B) ----
+  Tens x = b.conv("backbone.firstconv.0", img, 2, 2, 1, true, nullptr);
+  Tens y = b.conv("backbone.firstconv.1", x, 2, 1, 1, true, nullptr); b.free(x);
+  x = b.conv("backbone.firstconv.2", y, 2, 2, 1, true, nullptr); b.free(y);
+  b.tap("firstconv", x, 2);
+  const int strides[4] = {1, K >= 3 ? 2 : 1, K >= 4 ? 2 : 1, 1};
+  Tens l3, l4;
+  for (int li = 1; li <= 4; ++li) {
+    for (int bi = 0; bi < LAYER_BLOCKS[li - 1]; ++bi) {
+      const std::string p = "backbone.layer" + std::to_string(li) + "." + std::to_string(bi);
+      const int s = bi == 0 ? strides[li - 1] : 1, dil = li == 4 ? 2 : 1;
+      Tens a = b.conv(p + ".conv_a", x, 2, s, dil, true, nullptr);
+      Tens sc = x;
+      const bool ds = bi == 0 && li <= 3;
+      if (ds) sc = b.conv(p + ".downsample", x, 2, s, 1, false, nullptr);
+      Tens o = b.conv(p + ".conv_b", a, 2, 1, dil, true, &sc);
+      b.free(a);
+      if (ds) b.free(sc);
+      if (!(li == 4 && bi == 0)) b.free(x);      // layer3's output stays alive for the gwc concat
+      x = o;
+    }
+    b.tap("layer" + std::to_string(li), x, 2);
+    if (li == 3) l3 = x;
+    if (li == 4) l4 = x;
+  }
+  (void)LAYER_CH;
+  // gwc feature = cat(layer3, layer4) along channels: [2B][32][h][w][8]
+  Tens gwc = b.alloc(2, 256, 1, h, w);
+  {
+    Op op; op.name = "gwc_concat";
+    const size_t half = (size_t)16 * h * w * 8 * sizeof(float);
+    float* dst = gwc.p; const float* s3 = l3.p; const float* s4 = l4.p;
+    op.fn = [=](int B, cudaStream_t st) {
+      cudaError_t e = cudaMemcpy2DAsync(dst, 2 * half, s3, half, half, 2 * B, cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) return e;
+      return cudaMemcpy2DAsync(reinterpret_cast<char*>(dst) + half, 2 * half, s4, half, half, 2 * B,
+                               cudaMemcpyDeviceToDevice, st);
+    };
+    op.bytes = 4.0 * half;
+    c->ops.push_back(op);
+  }
+  b.free(l3); b.free(l4);
+  b.tap("gwc", gwc, 2);
+  Tens lc = b.conv("backbone.lastconv.0", gwc, 2, 1, 1, true, nullptr);
+  Tens cat = b.conv("backbone.lastconv.1", lc, 2, 1, 1, false, nullptr); b.free(lc);
+  b.tap("cat", cat, 2);
+
+  // ---- M2 cost volume [B][8][D][h][w][8] ----
+  Tens vol = b.alloc(1, 64, D, h, w);
+  {
+    Op op; op.name = "costvol";
+    op.fn = [=](int B, cudaStream_t st) { return launch_costvol(gwc, cat, vol, B, D, st); };
+    op.flops = 2.0 * 256 * D * h * w;
+    op.bytes = 4.0 * (2.0 * (256 + 16) * h * w + 64.0 * D * h * w);
+    c->ops.push_back(op);
+  }
+  b.free(gwc); b.free(cat);
+  b.tap("volume", vol, 1);
+
+  // ---- M3 3-D aggregation ----
+  Tens v = vol;
+  for (int i = 0; i < 5; ++i) {
+    Tens o = b.conv("head.filter." + std::to_string(i), v, 1, 1, 1, true, nullptr);
+    b.free(v); v = o;
+    b.tap("filter" + std::to_string(i), v, 1);
+  }
+  Plane cost = b.conv_to1("head.conv3d_alone", v, 1, false, nullptr, 1); b.free(v);
+  b.tap("cost", cost);
+
+  // ---- M4 soft-argmin ----
+  Plane disp = b.palloc(1, h, w);
+  {
+    Op op; op.name = "softargmin";
+    op.fn = [=](int B, cudaStream_t st) { Plane cc = cost; cc.n = B; return launch_softargmin(cc, disp, st); };
+    op.bytes = 4.0 * (D + 1.0) * h * w;
+    c->ops.push_back(op);
+  }
+  b.free(cost);
+  b.tap("disp0", disp);
+
+  // ---- M5 edge-aware refinement x K ----
+  for (int s = 0; s < K; ++s) {
+    const std::string p = "head.refine." + std::to_string(s);
+    const int hs = disp.h * 2, ws = disp.w * 2;
+    Tens rin = b.alloc(1, 4, 1, hs, ws);
+    {
+      Op op; op.name = p + ".in";
+      Plane dsrc = disp;
+      op.fn = [=](int B, cudaStream_t st) { return launch_refine_in(dsrc, img, rin, B, st); };
+      op.bytes = 4.0 * (disp.h * disp.w + 3.0 * hs * ws + 8.0 * hs * ws);
+      c->ops.push_back(op);
+    }
+    Tens f = b.conv(p + ".conv_in", rin, 1, 1, 1, true, nullptr);
+    for (int bi = 0; bi < 6; ++bi) {
+      const std::string q = p + ".blocks." + std::to_string(bi);
+      Tens a = b.conv(q + ".conv_a", f, 1, 1, REF_DIL[bi], true, nullptr);
+      Tens o = b.conv(q + ".conv_b", a, 1, 1, REF_DIL[bi], true, &f);
+      b.free(a); b.free(f); f = o;
+    }
+    b.tap("refine" + std::to_string(s) + ".feat", f, 1);
+    Plane nd = b.conv_to1(p + ".conv_out", f, 1, true, rin.p, 8);
+    b.free(f); b.free(rin); b.free(disp);
+    disp = nd;
+    b.tap("disp" + std::to_string(s + 1), disp);
+  }
+  c->disp_final = disp;
+  if (b.fail) {
+    if (!c->err[0]) snprintf(c->err, sizeof(c->err), "device allocation failed while building the plan");
+    return SNB_ERR_NOMEM;
+  }
+  return SNB_OK;
+}
+
+int run_plan(snb_ctx* c, int B, cudaStream_t st, bool use_graph) {
+  if (use_graph) {
+    auto it = c->graphs.find(B);
+    if (it == c->graphs.end()) {
+      cudaGraph_t g = nullptr;
+      if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return SNB_ERR_CUDA;
+      cudaError_t e = cudaSuccess;
+      for (auto& op : c->ops) { e = op.fn(B, st); if (e != cudaSuccess) break; }
+      cudaError_t e2 = cudaStreamEndCapture(st, &g);
+      if (e != cudaSuccess || e2 != cudaSuccess) {
+        snprintf(c->err, sizeof(c->err), "graph capture failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+        if (g) cudaGraphDestroy(g);
+        return SNB_ERR_CUDA;
+      }
+      cudaGraphExec_t ge = nullptr;
+      if (cudaGraphInstantiate(&ge, g, 0) != cudaSuccess) { cudaGraphDestroy(g); return SNB_ERR_CUDA; }
+      cudaGraphDestroy(g);
+      it = c->graphs.emplace(B, ge).first;
+    }
+    if (cudaGraphLaunch(it->second, st) != cudaSuccess) {
+      snprintf(c->err, sizeof(c->err), "cudaGraphLaunch: %s", cudaGetErrorString(cudaGetLastError()));
+      return SNB_ERR_CUDA;
+    }
+    return SNB_OK;
+  }
+  for (auto& op : c->ops) {
+    cudaError_t e = op.fn(B, st);
+    if (e != cudaSuccess) {
+      snprintf(c->err, sizeof(c->err), "%s: %s", op.name.c_str(), cudaGetErrorString(e));
+      return SNB_ERR_CUDA;
+    }
+  }
+  return SNB_OK;
+}
+
+void free_ctx(snb_ctx* c) {
+  for (auto& g : c->graphs) cudaGraphExecDestroy(g.second);
+  c->graphs.clear();
+  c->arena.release_all();
+  for (void* p : c->wallocs) cudaFree(p);
+  c->wallocs.clear();
+  if (c->d_in) cudaFree(c->d_in);
+  if (c->d_out) cudaFree(c->d_out);
+  if (c->d_frames) cudaFree(c->d_frames);
+  for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+}
+
+}  // namespace snb

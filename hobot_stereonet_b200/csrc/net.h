@@ -1,0 +1,106 @@
+// Context of one B200-resident StereoNet model instance: weights, scratch arena, static op plan.
+// Replaces the state the closed dnn_node runtime keeps behind DnnNode::{Init,GetModel,Run}
+// (stereonet_node.cpp:44,51,812).
+#pragma once
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/snb200.h"
+#include "common.cuh"
+
+namespace snb {
+
+struct HostTensor {
+  std::vector<int> shape;
+  std::vector<float> data;
+};
+
+struct ConvW {             // device-resident, kernel-specific packing of one convolution
+  float* w = nullptr;      // direct: [cc][cb][kz][tap][8][CO]; to1: [cb][kz][9][8]
+  float* b = nullptr;      // [cout]
+  float b0 = 0.f;          // bias of Cout=1 convs
+  int cout = 0, cin = 0, ks = 1, kz = 1;
+};
+
+struct Op {
+  std::string name;
+  std::function<cudaError_t(int B, cudaStream_t)> fn;
+  double flops = 0;        // algorithmic FLOPs per stereo pair
+  double bytes = 0;        // algorithmic HBM bytes per stereo pair
+};
+
+struct Stage {             // named tap for snb_debug_read
+  bool is_plane = false;
+  Tens t;
+  Plane p;
+  int nmul = 1;            // tensor batch = nmul * B
+};
+
+struct Arena {
+  struct Blk { void* p; size_t bytes; bool free; };
+  std::vector<Blk> blks;
+  bool reuse = true;
+  size_t total = 0;
+  void* get(size_t bytes);
+  void put(void* p);
+  void release_all();
+};
+
+struct Task {
+  const int8_t* in; int32_t* out; int batch; snb_done_fn done; void* user;
+};
+
+}  // namespace snb
+
+struct snb_ctx {
+  snb_config cfg{};
+  std::string model_file;
+  int H = 0, W = 0, K = 0, D = 0, Hp = 0, Wp = 0, h = 0, w = 0, maxB = 1;
+  float qmul = 0.f;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
+  int blob_K = -1;
+  std::map<std::string, snb::HostTensor> wts;
+  std::map<std::string, snb::ConvW> convs;
+  std::vector<void*> wallocs;
+
+  snb::Arena arena;
+  std::vector<snb::Op> ops;
+  std::map<std::string, snb::Stage> stages;
+  snb::Tens img;                       // C8 input image [2B][1][Hp][Wp][8]
+  snb::Plane disp_final;               // [B][Hp][Wp]
+  int8_t* d_in = nullptr;              // s8 [maxB][6][H][W]
+  int32_t* d_out = nullptr;            // s32 [maxB][H][W]
+  uint8_t* d_frames = nullptr;         // NV12 frames [maxB][H*3/2][2W]
+  size_t in_bytes = 0, out_bytes = 0, frame_bytes = 0;   // per pair
+
+  std::map<int, cudaGraphExec_t> graphs;   // by batch
+  int last_B = 0;
+
+  // async tasks (task_num in flight; callbacks on the worker thread = the reference's PostProcess thread)
+  std::thread worker;
+  std::mutex mu, run_mu;
+  std::condition_variable cv_push, cv_pop;
+  std::deque<snb::Task> queue;
+  int inflight = 0;
+  bool stop = false;
+
+  snb_rt_stat stat{};
+  double fps_t0 = 0; int fps_in = 0, fps_out = 0;
+  mutable char err[512] = {0};
+};
+
+namespace snb {
+int parse_blob(snb_ctx* c, const void* blob, size_t bytes);
+int upload_weights(snb_ctx* c);
+int build_plan(snb_ctx* c);
+int run_plan(snb_ctx* c, int B, cudaStream_t st, bool use_graph);
+void free_ctx(snb_ctx* c);
+}  // namespace snb

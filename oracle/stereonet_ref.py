@@ -105,7 +105,7 @@ class Oracle:
 
     def soft_argmin(self, cost):
         p = torch.softmax(cost, dim=1)
-        d = torch.arange(self.cfg.D, dtype=torch.float32).view(1, -1, 1, 1) / self.cfg.D
+        d = torch.arange(self.cfg.D, dtype=torch.float32, device=cost.device).view(1, -1, 1, 1) / self.cfg.D
         return (p * d).sum(1, keepdim=True)                             # [B,1,h,w] in [0,1)
 
     def refine(self, disp, left, s, dump=None):
@@ -128,7 +128,12 @@ class Oracle:
         """s8 [B,6,H,W] int8 -> normalised disparity [B,Hp,Wp] float32 (disp_px / max_disp)."""
         cfg = self.cfg
         assert s8.dtype == np.int8 and s8.shape[1:] == (6, cfg.H, cfg.W), s8.shape
-        x = torch.from_numpy(s8.astype(np.float32)) * IN_SCALE
+        return self.forward_float(torch.from_numpy(s8.astype(np.float32)) * IN_SCALE, dump)
+
+    @torch.no_grad()
+    def forward_float(self, x: torch.Tensor, dump: Optional[dict] = None) -> torch.Tensor:
+        """x [B,6,H,W] float32 (= s8/128) -> normalised disparity [B,Hp,Wp]."""
+        cfg = self.cfg
         x = F.pad(x, (0, cfg.Wp - cfg.W, 0, cfg.Hp - cfg.H))
         B = x.shape[0]
         left, right = x[:, :3], x[:, 3:]
