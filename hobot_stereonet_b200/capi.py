@@ -73,6 +73,7 @@ def load() -> C.CDLL:
         "snb_pre_quantize": (C.c_int8, [C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]),
         "snb_post_pack": (i64, [vp, u64, vp, u64, vp, u64]),
         "snb_post_parse_depth": (C.c_int, [vp, i64, C.c_float, vp]),
+        "snb_weights_synthesize": (i64, [i32, u64, vp, u64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -215,6 +216,18 @@ class Model:
         arr = (SnbKernelTime * 512)()
         n = self._check(self._l.snb_profile_pass(self._h, batch, arr, 512))
         return [(arr[i].name.decode(), arr[i].ms, arr[i].flops, arr[i].bytes) for i in range(n)]
+
+
+def synthesize_weights(K: int, seed: int = 1234) -> bytes:
+    """Seeded synthetic weight blob (SNB2WGT1) made by the library itself."""
+    n = lib().snb_weights_synthesize(K, seed, None, 0)
+    if n < 0:
+        raise SnbError(int(n), "snb_weights_synthesize")
+    buf = C.create_string_buffer(n)
+    n2 = lib().snb_weights_synthesize(K, seed, C.cast(buf, C.c_void_p), n)
+    if n2 != n:
+        raise SnbError(int(n2), "snb_weights_synthesize")
+    return buf.raw
 
 
 # ---- host-side byte formats (no GPU involved) ---------------------------------------------------

@@ -97,6 +97,10 @@ SNB_API void snb_destroy(snb_ctx* ctx);
  * every rank installs it).  `blob` may be a device pointer when is_device != 0. */
 SNB_API int snb_set_weights(snb_ctx* ctx, const void* blob, uint64_t bytes, int is_device);
 
+/* Seeded synthetic weight blob for refinement-stage count K (the reference's float weights are not
+ * recoverable from its BPU binary).  dst == NULL: returns the size needed.  Host-only, no GPU. */
+SNB_API int64_t snb_weights_synthesize(int32_t K, uint64_t seed, void* dst, uint64_t cap);
+
 /* ---- hbDNNGet{Input,Output}TensorProperties / GetModelInputSize (stereonet_node.cpp:45,78,94) --- */
 SNB_API int snb_get_io(const snb_ctx* ctx, snb_tensor_props* in, snb_tensor_props* out);
 SNB_API int snb_get_model_input_size(const snb_ctx* ctx, int32_t input_index, int32_t* w, int32_t* h);

@@ -96,3 +96,19 @@ def test_create_checks_model_file_first(built_lib):
     with pytest.raises(SnbError) as e:
         Model(63, 96, 3, 8, weights=b"x" * 64)
     assert e.value.code == capi.SNB_ERR_INVALID
+
+
+def test_synthesized_blob_matches_oracle_layer_table(built_lib):
+    """The library's own layer table (weights_host.cpp) and the oracle's (oracle/arch.py) agree."""
+    from hobot_stereonet_b200 import capi
+    from oracle import arch
+    for K in (2, 3, 4):
+        k2, w = weights.from_blob(capi.synthesize_weights(K, 7))
+        ref = weights.generate(K)
+        assert k2 == K and list(w.keys()) == list(ref.keys())
+        assert all(w[n].shape == ref[n].shape for n in w)
+        for spec in arch.conv_specs(K):
+            fan_in = spec.cin * int(np.prod(spec.k))
+            std = w[spec.name + ".weight"].std()
+            assert abs(std / (spec.gain * np.sqrt(2.0 / fan_in)) - 1) < 0.25, spec.name
+    assert capi.synthesize_weights(3, 7) == capi.synthesize_weights(3, 7) != capi.synthesize_weights(3, 8)
