@@ -71,6 +71,7 @@ int snb_create(snb_ctx** out, const snb_config* cfg) {
   if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, SNB_ERR_INVALID, "snb_create: bad device ordinal");
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, cfg->device);
+  const int num_sms = prop.multiProcessorCount;
   if (prop.major != 10) {
     snprintf(g_err, sizeof(g_err), "snb_create: device %d is sm_%d%d; this build carries sm_100a code only", cfg->device, prop.major, prop.minor);
     return SNB_ERR_CUDA;
@@ -80,6 +81,7 @@ int snb_create(snb_ctx** out, const snb_config* cfg) {
   c->cfg = *cfg;
   if (cfg->model_file) c->model_file = cfg->model_file;
   c->cfg.model_file = nullptr; c->cfg.weights = nullptr;
+  c->num_sms = num_sms;
   c->H = cfg->height; c->W = cfg->width; c->K = cfg->K; c->D = cfg->D; c->maxB = cfg->max_batch;
   const int s = 1 << c->K;
   c->Hp = (c->H + s - 1) / s * s; c->Wp = (c->W + s - 1) / s * s;
@@ -300,9 +302,21 @@ int64_t snb_debug_read(snb_ctx* c, const char* name, float* dst, uint64_t cap, i
   if (shape) { shape[0] = N; shape[1] = t.c; shape[2] = t.d; shape[3] = t.h; shape[4] = t.w; }
   if (!dst) return (int64_t)n;
   if (cap < n) return SNB_ERR_INVALID;
-  std::vector<float> tmp((size_t)N * t.cb * t.d * t.h * t.w * 8);
-  CK(c, cudaMemcpy(tmp.data(), t.p, tmp.size() * 4, cudaMemcpyDeviceToHost));
   const size_t sp = (size_t)t.d * t.h * t.w;
+  if (t.planes == 2) {
+    std::vector<__half> tmp((size_t)N * 2 * t.cb * sp * 8);
+    CK(c, cudaMemcpy(tmp.data(), t.p, tmp.size() * 2, cudaMemcpyDeviceToHost));
+    for (int nn = 0; nn < N; ++nn)
+      for (int ch = 0; ch < t.c; ++ch) {
+        const __half* hi = tmp.data() + (((size_t)(nn * 2) * t.cb + ch / 8) * sp) * 8 + ch % 8;
+        const __half* lo = hi + (size_t)t.cb * sp * 8;
+        float* d = dst + ((size_t)nn * t.c + ch) * sp;
+        for (size_t i = 0; i < sp; ++i) d[i] = __half2float(hi[i * 8]) + __half2float(lo[i * 8]);
+      }
+    return (int64_t)n;
+  }
+  std::vector<float> tmp((size_t)N * t.cb * sp * 8);
+  CK(c, cudaMemcpy(tmp.data(), t.p, tmp.size() * 4, cudaMemcpyDeviceToHost));
   for (int nn = 0; nn < N; ++nn)
     for (int ch = 0; ch < t.c; ++ch) {
       const float* src = tmp.data() + (((size_t)nn * t.cb + ch / 8) * sp) * 8 + ch % 8;

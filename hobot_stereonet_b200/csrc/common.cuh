@@ -5,18 +5,33 @@
 // stages; the cost volume and the 3-D aggregation use d = D.  Disparity maps and the cost tensor
 // are plain fp32 planes [n][(d)][h][w].
 #pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
+
+#include <vector>
 
 namespace snb {
 
+// Two storage types share the C8 indexing:
+//   planes == 1 : fp32                                  [n][cb][d][h][w][8]      (SNB_PREC_FP32)
+//   planes == 2 : split fp16, x = hi + lo, two planes   [n][2][cb][d][h][w][8]   (SNB_PREC_TC_F16X2)
+// Both cost 4 bytes per element.
 struct Tens {            // C8 activation tensor
-  float* p = nullptr;
+  void* p = nullptr;
   int n = 0, cb = 0, d = 1, h = 0, w = 0;
   int c = 0;             // logical channels (<= cb*8)
+  int planes = 1;
+  float* f() const { return static_cast<float*>(p); }
+  __half* hp() const { return static_cast<__half*>(p); }
+  size_t plane_elems() const { return (size_t)cb * d * h * w * 8; }       // one (n[,hl]) slab
+  size_t sample_stride() const { return plane_elems() * planes; }          // elements between samples
+  size_t lo_off() const { return planes == 2 ? plane_elems() : 0; }
   size_t elems() const { return (size_t)n * cb * d * h * w * 8; }
-  size_t bytes() const { return elems() * sizeof(float); }
+  size_t bytes() const { return elems() * 4; }
 };
 
 struct Plane {           // dense fp32 [n][d][h][w]
@@ -27,22 +42,41 @@ struct Plane {           // dense fp32 [n][d][h][w]
 };
 
 struct ConvParams {
-  const float* in; float* out; const float* w; const float* bias;
-  const float* res;      // residual added before the activation (same layout as out) or nullptr
+  const void* in; void* out; const float* w; const float* bias;
+  const void* res;       // residual added before the activation (same layout as out) or nullptr
   int N, CBin, Din, Hin, Win;
   int CBout, Dout, Hout, Wout;
   int ks;                // spatial kernel size 1 or 3
   int kz;                // depth taps 1 (2-D) or 3 (3-D, pad 1)
   int stride, dil, relu;
   int tiles_x;
+  size_t in_ss, in_lo, out_ss, out_lo;   // sample strides / hi->lo plane offsets (elements), see Tens
+  int half;              // 0: fp32 storage, 1: split-fp16 storage
 };
 
 struct ConvTo1Params {   // Cout = 1 convolutions (conv3d_alone, refinement conv_out)
-  const float* in; float* out; const float* w; float bias;
-  const float* res; int res_stride;   // residual element stride (8 when it is channel 0 of a C8 tensor)
+  const void* in; float* out; const float* w; float bias;
+  const void* res; int res_c8;        // residual: fp32 plane (res_c8 = 0) or channel 0 of a C8 tensor of in's storage type
   int N, CBin, D, H, W;
   int kz, dil, relu;
+  size_t in_ss, in_lo;
+  size_t res_ss, res_lo;              // residual C8 tensor: sample stride / hi->lo offset (elements)
+  int half;
 };
+
+struct TcConvParams {    // k_conv_tc.cu
+  const __half* w; const float* bias; const __half* res; __half* out;
+  int N, D, H, W, CBin, CBout;
+  int dil, kz, relu;
+  int nky;               // kernel rows per pipeline stage: 3 (full halo tile) or 1 (row group, large dilation)
+  int nk16;              // Cin / 16
+  int NT, R;             // output channels / image rows per tile
+  int BW, BH;            // TMA box (pixels)
+  int tiles_x, tiles_y, ccs, total_tiles;
+  int nstages;
+  uint32_t a_bytes, w_bytes, tx_bytes;
+};
+struct TcConvPlan { CUtensorMap tm_in; TcConvParams p; size_t smem; };
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 

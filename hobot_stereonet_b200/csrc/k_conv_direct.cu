@@ -8,10 +8,11 @@
 // Covers: SURVEY.md §8a rows M1 (backbone), M3 (Conv3d as kz=3 stacked depth taps), M5 (refinement).
 #include "common.cuh"
 #include "kernels.cuh"
+#include "store.cuh"
 
 namespace snb {
 
-template <int COT>
+template <int COT, typename T>
 __global__ void __launch_bounds__(256) k_conv_direct(ConvParams p) {
   constexpr int CO = 4 * COT;               // output channels per CTA
   extern __shared__ float smem[];
@@ -43,14 +44,13 @@ __global__ void __launch_bounds__(256) k_conv_direct(ConvParams p) {
       const int zin = dz + kz - (p.kz >> 1);
       if (zin < 0 || zin >= p.Din) continue;          // uniform across the CTA
       __syncthreads();
-      const float* src = p.in + (((size_t)n * p.CBin + cb) * p.Din + zin) * in_slice;
-      for (int i = tid; i < IH * IW * 2; i += 256) {  // float4 granularity: 2 per pixel
-        const int pix = i >> 1, hv = i & 1;
+      const size_t src = (size_t)n * p.in_ss + ((size_t)cb * p.Din + zin) * in_slice;
+      for (int pix = tid; pix < IH * IW; pix += 256) {
         const int y = iy0 + pix / IW, x = ix0 + pix % IW;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (y >= 0 && y < p.Hin && x >= 0 && x < p.Win)
-          v = __ldg(reinterpret_cast<const float4*>(src + ((size_t)y * p.Win + x) * 8) + hv);
-        reinterpret_cast<float4*>(s_in)[i] = v;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (y >= 0 && y < p.Hin && x >= 0 && x < p.Win) St<T>::ld8(p.in, src + ((size_t)y * p.Win + x) * 8, p.in_lo, v);
+        reinterpret_cast<float4*>(s_in)[2 * pix] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(s_in)[2 * pix + 1] = make_float4(v[4], v[5], v[6], v[7]);
       }
       const float* wsrc = p.w + ((((size_t)cc * p.CBin + cb) * p.kz + kz) * ntap) * 8 * CO;
       for (int i = tid; i < ntap * 8 * CO / 4; i += 256)
@@ -89,35 +89,67 @@ __global__ void __launch_bounds__(256) k_conv_direct(ConvParams p) {
     }
   }
 
-  // epilogue: bias (+ residual) (+ ReLU); thread's COT channels sit inside one C8 block
+  // epilogue: bias (+ residual) (+ ReLU).  A thread's COT channels sit inside one C8 block; for COT = 4 two
+  // neighbouring channel groups (cg, cg^1) share a block, so the pair is exchanged through shared memory.
   const int co0 = cc * CO + cg * COT;       // first output channel of this thread
-  const int cbo = co0 >> 3, cin8 = co0 & 7;
   float bv[COT];
 #pragma unroll
   for (int c = 0; c < COT; ++c) bv[c] = __ldg(p.bias + co0 + c);
+  if constexpr (COT == 8) {
+    const int cbo = co0 >> 3;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int idx = i * 64 + half * 32 + lane;
-    const int y = ty0 + (idx >> 4), x = tx0 + (idx & 15);
-    if (y >= p.Hout || x >= p.Wout) continue;
-    const size_t o = (((((size_t)n * p.CBout + cbo) * p.Dout + dz) * p.Hout + y) * p.Wout + x) * 8 + cin8;
-    float v[COT];
+    for (int i = 0; i < 4; ++i) {
+      const int idx = i * 64 + half * 32 + lane;
+      const int y = ty0 + (idx >> 4), x = tx0 + (idx & 15);
+      if (y >= p.Hout || x >= p.Wout) continue;
+      const size_t o = (size_t)n * p.out_ss + ((((size_t)cbo * p.Dout + dz) * p.Hout + y) * p.Wout + x) * 8;
+      float v[8];
 #pragma unroll
-    for (int c = 0; c < COT; ++c) v[c] = acc[i][c] + bv[c];
-    if (p.res) {
+      for (int c = 0; c < 8; ++c) v[c] = acc[i][c] + bv[c];
+      if (p.res) {
+        float r[8];
+        St<T>::ld8(p.res, o, p.out_lo, r);
 #pragma unroll
-      for (int c4 = 0; c4 < COT / 4; ++c4) {
-        const float4 r = __ldg(reinterpret_cast<const float4*>(p.res + o) + c4);
-        v[c4 * 4 + 0] += r.x; v[c4 * 4 + 1] += r.y; v[c4 * 4 + 2] += r.z; v[c4 * 4 + 3] += r.w;
+        for (int c = 0; c < 8; ++c) v[c] += r[c];
       }
-    }
-    if (p.relu) {
+      if (p.relu) {
 #pragma unroll
-      for (int c = 0; c < COT; ++c) v[c] = fmaxf(v[c], 0.f);
+        for (int c = 0; c < 8; ++c) v[c] = fmaxf(v[c], 0.f);
+      }
+      St<T>::st8(p.out, o, p.out_lo, v);
     }
+  } else {
+    // COT == 4: stage the tile through shared memory as [pixel 256][16 ch], then write whole blocks
+    __syncthreads();
+    float* s_o = smem;
 #pragma unroll
-    for (int c4 = 0; c4 < COT / 4; ++c4)
-      reinterpret_cast<float4*>(p.out + o)[c4] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+    for (int i = 0; i < 4; ++i) {
+      const int idx = i * 64 + half * 32 + lane;
+#pragma unroll
+      for (int c = 0; c < COT; ++c) s_o[idx * CO + cg * COT + c] = acc[i][c] + bv[c];
+    }
+    __syncthreads();
+    for (int e = tid; e < 256 * (CO / 8); e += 256) {
+      const int idx = e / (CO / 8), blk = e % (CO / 8);
+      const int y = ty0 + (idx >> 4), x = tx0 + (idx & 15);
+      if (y >= p.Hout || x >= p.Wout) continue;
+      const int cbo = (cc * CO >> 3) + blk;
+      const size_t o = (size_t)n * p.out_ss + ((((size_t)cbo * p.Dout + dz) * p.Hout + y) * p.Wout + x) * 8;
+      float v[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[c] = s_o[idx * CO + blk * 8 + c];
+      if (p.res) {
+        float r[8];
+        St<T>::ld8(p.res, o, p.out_lo, r);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] += r[c];
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = fmaxf(v[c], 0.f);
+      }
+      St<T>::st8(p.out, o, p.out_lo, v);
+    }
   }
 }
 
@@ -132,12 +164,25 @@ cudaError_t launch_conv_direct(ConvParams p, int cout, cudaStream_t st) {
   const int tiles = p.tiles_x * cdiv(p.Hout, 16);
   if (cout % 32 == 0) {
     const size_t sm = conv_direct_smem(p, 32);
-    if (need_attr(0)) cudaFuncSetAttribute(k_conv_direct<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    k_conv_direct<8><<<dim3(tiles, cout / 32, p.N * p.Dout), 256, sm, st>>>(p);
+    const dim3 g(tiles, cout / 32, p.N * p.Dout);
+    if (p.half) {
+      if (need_attr(3)) cudaFuncSetAttribute(k_conv_direct<8, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      k_conv_direct<8, __half><<<g, 256, sm, st>>>(p);
+    } else {
+      if (need_attr(0)) cudaFuncSetAttribute(k_conv_direct<8, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      k_conv_direct<8, float><<<g, 256, sm, st>>>(p);
+    }
   } else if (cout % 16 == 0) {
-    const size_t sm = conv_direct_smem(p, 16);
-    if (need_attr(1)) cudaFuncSetAttribute(k_conv_direct<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    k_conv_direct<4><<<dim3(tiles, cout / 16, p.N * p.Dout), 256, sm, st>>>(p);
+    size_t sm = conv_direct_smem(p, 16);
+    if (sm < 256 * 16 * sizeof(float)) sm = 256 * 16 * sizeof(float);      // epilogue staging
+    const dim3 g(tiles, cout / 16, p.N * p.Dout);
+    if (p.half) {
+      if (need_attr(4)) cudaFuncSetAttribute(k_conv_direct<4, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      k_conv_direct<4, __half><<<g, 256, sm, st>>>(p);
+    } else {
+      if (need_attr(1)) cudaFuncSetAttribute(k_conv_direct<4, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      k_conv_direct<4, float><<<g, 256, sm, st>>>(p);
+    }
   } else {
     return cudaErrorInvalidValue;
   }
@@ -145,6 +190,7 @@ cudaError_t launch_conv_direct(ConvParams p, int cout, cudaStream_t st) {
 }
 
 // ---- Cout = 1: one thread per output element, weights in shared memory --------------------------
+template <typename T>
 __global__ void __launch_bounds__(256) k_conv_to1(ConvTo1Params p) {
   extern __shared__ float s_w[];            // [CBin][kz][9][8]
   const int nw = p.CBin * p.kz * 9 * 8;
@@ -160,7 +206,7 @@ __global__ void __launch_bounds__(256) k_conv_to1(ConvTo1Params p) {
     for (int kz = 0; kz < p.kz; ++kz) {
       const int zin = dz + kz - (p.kz >> 1);
       if (zin < 0 || zin >= p.D) continue;
-      const float* src = p.in + (((size_t)n * p.CBin + cb) * p.D + zin) * slice;
+      const size_t src = (size_t)n * p.in_ss + ((size_t)cb * p.D + zin) * slice;
       const float* wp = s_w + ((cb * p.kz + kz) * 9) * 8;
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
@@ -170,26 +216,29 @@ __global__ void __launch_bounds__(256) k_conv_to1(ConvTo1Params p) {
         for (int kx = 0; kx < 3; ++kx) {
           const int xx = x + (kx - 1) * p.dil;
           if (xx < 0 || xx >= p.W) continue;
-          const float4* ip = reinterpret_cast<const float4*>(src + ((size_t)yy * p.W + xx) * 8);
-          const float4 v0 = __ldg(ip), v1 = __ldg(ip + 1);
+          float v[8];
+          St<T>::ld8(p.in, src + ((size_t)yy * p.W + xx) * 8, p.in_lo, v);
           const float* w8 = wp + (ky * 3 + kx) * 8;
-          acc = fmaf(v0.x, w8[0], acc); acc = fmaf(v0.y, w8[1], acc);
-          acc = fmaf(v0.z, w8[2], acc); acc = fmaf(v0.w, w8[3], acc);
-          acc = fmaf(v1.x, w8[4], acc); acc = fmaf(v1.y, w8[5], acc);
-          acc = fmaf(v1.z, w8[6], acc); acc = fmaf(v1.w, w8[7], acc);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc = fmaf(v[c], w8[c], acc);
         }
       }
     }
   }
   const size_t o = (((size_t)n * p.D + dz) * p.H + y) * p.W + x;
-  if (p.res) acc += __ldg(p.res + o * p.res_stride);
+  if (p.res) {
+    if (p.res_c8) acc += St<T>::ld1(p.res, (size_t)n * p.res_ss + ((size_t)y * p.W + x) * 8, p.res_lo);
+    else acc += __ldg(static_cast<const float*>(p.res) + o);
+  }
   if (p.relu) acc = fmaxf(acc, 0.f);
   p.out[o] = acc;
 }
 
 cudaError_t launch_conv_to1(const ConvTo1Params& p, cudaStream_t st) {
   const size_t sm = (size_t)p.CBin * p.kz * 9 * 8 * sizeof(float);
-  k_conv_to1<<<dim3(cdiv(p.W, 32), cdiv(p.H, 8), p.N * p.D), 256, sm, st>>>(p);
+  const dim3 g(cdiv(p.W, 32), cdiv(p.H, 8), p.N * p.D);
+  if (p.half) k_conv_to1<__half><<<g, 256, sm, st>>>(p);
+  else k_conv_to1<float><<<g, 256, sm, st>>>(p);
   return cudaGetLastError();
 }
 

@@ -3,34 +3,36 @@
 // 128-bit accesses where the layout allows, shared-memory staging where data is reused across D.
 #include "common.cuh"
 #include "kernels.cuh"
+#include "store.cuh"
 
 namespace snb {
 
 // ------------------------------------------------------------------------------------------------
 // s8 NCHW [B,6,H,W] -> C8 image [2B][1][Hp][Wp][8].  Restates the tensor semantics the BPU model
 // gives its input: value = s8 * (1/128) (preprocess.cpp:1037), channels 0-2 left, 3-5 right.
-__global__ void k_pre_s8(const int8_t* __restrict__ s8, float* __restrict__ img, int B, int H, int W,
+template <typename T>
+__global__ void k_pre_s8(const int8_t* __restrict__ s8, void* __restrict__ img, size_t ss, size_t lo, int B, int H, int W,
                          int Hp, int Wp) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int n = blockIdx.z;                  // 0..2B-1
   if (x >= Wp) return;
   const int b = n % B, view = n / B;
-  float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (x < W && y < H) {
     const int8_t* src = s8 + (((size_t)b * 6 + view * 3) * H + y) * W + x;
     const size_t plane = (size_t)H * W;
-    v0.x = (float)src[0] * 0.0078125f;
-    v0.y = (float)src[plane] * 0.0078125f;
-    v0.z = (float)src[2 * plane] * 0.0078125f;
+    v[0] = (float)src[0] * 0.0078125f;
+    v[1] = (float)src[plane] * 0.0078125f;
+    v[2] = (float)src[2 * plane] * 0.0078125f;
   }
-  float4* dst = reinterpret_cast<float4*>(img + (((size_t)n * Hp + y) * Wp + x) * 8);
-  dst[0] = v0;
-  dst[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  St<T>::st8(img, (size_t)n * ss + ((size_t)y * Wp + x) * 8, lo, v);
 }
 
 cudaError_t launch_pre_s8(const int8_t* s8, Tens img, int B, int H, int W, cudaStream_t st) {
-  k_pre_s8<<<dim3(cdiv(img.w, 128), img.h, 2 * B), 128, 0, st>>>(s8, img.p, B, H, W, img.h, img.w);
+  const dim3 g(cdiv(img.w, 128), img.h, 2 * B);
+  if (img.planes == 2) k_pre_s8<__half><<<g, 128, 0, st>>>(s8, img.p, img.sample_stride(), img.lo_off(), B, H, W, img.h, img.w);
+  else k_pre_s8<float><<<g, 128, 0, st>>>(s8, img.p, img.sample_stride(), img.lo_off(), B, H, W, img.h, img.w);
   return cudaGetLastError();
 }
 
@@ -38,14 +40,15 @@ cudaError_t launch_pre_s8(const int8_t* s8, Tens img, int B, int H, int W, cudaS
 // Side-by-side NV12 frame -> the same C8 image (and optionally the s8 tensor the reference builds).
 // Restates stereonet_node.cpp:702-738 (L/R split), preprocess.h:128-155 (YUV420TOYUV444 incl. the
 // I420-indexing quirk on NV12 data) and preprocess.cpp:1032-1040 (x-128) in one pass.
-__global__ void k_pre_nv12(const uint8_t* __restrict__ frames, float* __restrict__ img,
+template <typename T>
+__global__ void k_pre_nv12(const uint8_t* __restrict__ frames, void* __restrict__ img, size_t ss, size_t lo,
                            int8_t* __restrict__ s8, int B, int H, int W, int Hp, int Wp, int correct) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int n = blockIdx.z;
   if (x >= Wp) return;
   const int b = n % B, view = n / B;
-  float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float v0[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (x < W && y < H) {
     const uint8_t* f = frames + (size_t)b * (H * 3 / 2) * (2 * W) + view * W;   // this view's column window
     const int pitch = 2 * W;
@@ -63,23 +66,25 @@ __global__ void k_pre_nv12(const uint8_t* __restrict__ frames, float* __restrict
       v = f[(size_t)(H + kv / W) * pitch + kv % W];
     }
     const int8_t sy = (int8_t)(yy ^ 0x80), su = (int8_t)(u ^ 0x80), sv = (int8_t)(v ^ 0x80);
-    v0.x = (float)sy * 0.0078125f;
-    v0.y = (float)su * 0.0078125f;
-    v0.z = (float)sv * 0.0078125f;
+    v0[0] = (float)sy * 0.0078125f;
+    v0[1] = (float)su * 0.0078125f;
+    v0[2] = (float)sv * 0.0078125f;
     if (s8) {
       int8_t* d = s8 + (((size_t)b * 6 + view * 3) * H + y) * W + x;
       const size_t plane = (size_t)H * W;
       d[0] = sy; d[plane] = su; d[2 * plane] = sv;
     }
   }
-  float4* dst = reinterpret_cast<float4*>(img + (((size_t)n * Hp + y) * Wp + x) * 8);
-  dst[0] = v0;
-  dst[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  St<T>::st8(img, (size_t)n * ss + ((size_t)y * Wp + x) * 8, lo, v0);
 }
 
 cudaError_t launch_pre_nv12(const uint8_t* frames, Tens img, int8_t* s8, int B, int H, int W, int correct,
                             cudaStream_t st) {
-  k_pre_nv12<<<dim3(cdiv(img.w, 128), img.h, 2 * B), 128, 0, st>>>(frames, img.p, s8, B, H, W, img.h, img.w, correct);
+  const dim3 g(cdiv(img.w, 128), img.h, 2 * B);
+  if (img.planes == 2)
+    k_pre_nv12<__half><<<g, 128, 0, st>>>(frames, img.p, img.sample_stride(), img.lo_off(), s8, B, H, W, img.h, img.w, correct);
+  else
+    k_pre_nv12<float><<<g, 128, 0, st>>>(frames, img.p, img.sample_stride(), img.lo_off(), s8, B, H, W, img.h, img.w, correct);
   return cudaGetLastError();
 }
 
@@ -91,34 +96,45 @@ cudaError_t launch_pre_nv12(const uint8_t* frames, Tens img, int8_t* s8, int B, 
 //   vol block 4..7: group-wise correlation, group = one C8 block of the 256-ch feature:
 //                   mean_8( L[g][x][:] * R[g][x-d][:] ), zero where x < d
 // Thread (x, j): consecutive threads write consecutive floats of [x][j] -> fully coalesced stores.
-__global__ void __launch_bounds__(256) k_costvol(const float* __restrict__ gwc, const float* __restrict__ cat,
-                                                 float* __restrict__ vol, int B, int D, int h, int w) {
+struct CostvolParams {
+  const void* gwc; const void* cat; void* vol;
+  size_t g_ss, g_lo, c_ss, c_lo, v_ss, v_lo;
+  int B, D, h, w;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_costvol(CostvolParams p) {
   extern __shared__ float sm[];
   const int y = blockIdx.x, b = blockIdx.y, q = blockIdx.z;    // q in 0..3
+  const int w = p.w, h = p.h, D = p.D;
   const int pitch = w * 8 + 4;                                  // +4 floats: 8 blocks hit 8 distinct 16B lanes
   float* sL = sm;                  // [8][pitch]
   float* sR = sm + 8 * pitch;
   const size_t row = (size_t)w * 8;
-  for (int i = threadIdx.x; i < 8 * w * 2; i += blockDim.x) {
-    const int j = i / (w * 2), r = i % (w * 2);                 // r: float4 index inside the row of block j
-    const size_t gl = ((((size_t)b * 32 + q * 8 + j) * h + y) * row);
-    const size_t gr = ((((size_t)(B + b) * 32 + q * 8 + j) * h + y) * row);
-    reinterpret_cast<float4*>(sL + j * pitch)[r] = __ldg(reinterpret_cast<const float4*>(gwc + gl) + r);
-    reinterpret_cast<float4*>(sR + j * pitch)[r] = __ldg(reinterpret_cast<const float4*>(gwc + gr) + r);
+  for (int i = threadIdx.x; i < 8 * w; i += blockDim.x) {
+    const int j = i / w, x = i % w;
+    const size_t off = (((size_t)(q * 8 + j)) * h + y) * row + (size_t)x * 8;
+    float v[8];
+    St<T>::ld8(p.gwc, (size_t)b * p.g_ss + off, p.g_lo, v);
+    reinterpret_cast<float4*>(sL + j * pitch + x * 8)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(sL + j * pitch + x * 8)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    St<T>::ld8(p.gwc, (size_t)(p.B + b) * p.g_ss + off, p.g_lo, v);
+    reinterpret_cast<float4*>(sR + j * pitch + x * 8)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(sR + j * pitch + x * 8)[1] = make_float4(v[4], v[5], v[6], v[7]);
   }
   __syncthreads();
 
   const size_t vslice = (size_t)h * w * 8;                      // one (cb, d) slice
-  float* vg = vol + ((size_t)b * 8 + 4 + q) * D * vslice + (size_t)y * row;   // gwc block 4+q
-  float* vc = vol + ((size_t)b * 8 + q) * D * vslice + (size_t)y * row;       // concat block q
-  const float* csrc = cat + ((((size_t)((q >> 1) ? B + b : b)) * 2 + (q & 1)) * h + y) * row;
+  const size_t vg = (size_t)b * p.v_ss + (size_t)(4 + q) * D * vslice + (size_t)y * row;   // gwc block 4+q
+  const size_t vc = (size_t)b * p.v_ss + (size_t)q * D * vslice + (size_t)y * row;         // concat block q
+  const size_t csrc = (size_t)((q >> 1) ? p.B + b : b) * p.c_ss + ((size_t)(q & 1) * h + y) * row;
   const bool shifted = (q >> 1) != 0;
 
   for (int e = threadIdx.x; e < w * 8; e += blockDim.x) {
     const int x = e >> 3, j = e & 7;
     const float4 l0 = *reinterpret_cast<const float4*>(sL + j * pitch + x * 8);
     const float4 l1 = *reinterpret_cast<const float4*>(sL + j * pitch + x * 8 + 4);
-    const float cl = __ldg(csrc + e);                           // unshifted concat value (left blocks)
+    const float cl = St<T>::ld1(p.cat, csrc + e, p.c_lo);      // unshifted concat value (left blocks)
     for (int d = 0; d < D; ++d) {
       float g = 0.f, c = 0.f;
       if (x >= d) {
@@ -128,10 +144,10 @@ __global__ void __launch_bounds__(256) k_costvol(const float* __restrict__ gwc, 
         g = fmaf(l0.y, r0.y, g); g = fmaf(l0.z, r0.z, g); g = fmaf(l0.w, r0.w, g);
         g = fmaf(l1.x, r1.x, g); g = fmaf(l1.y, r1.y, g); g = fmaf(l1.z, r1.z, g); g = fmaf(l1.w, r1.w, g);
         g *= 0.125f;
-        c = shifted ? __ldg(csrc + e - d * 8) : cl;
+        c = shifted ? St<T>::ld1(p.cat, csrc + e - d * 8, p.c_lo) : cl;
       }
-      vg[(size_t)d * vslice + e] = g;
-      vc[(size_t)d * vslice + e] = c;
+      St<T>::st1(p.vol, vg + (size_t)d * vslice + e, p.v_lo, g);
+      St<T>::st1(p.vol, vc + (size_t)d * vslice + e, p.v_lo, c);
     }
   }
 }
@@ -139,8 +155,15 @@ __global__ void __launch_bounds__(256) k_costvol(const float* __restrict__ gwc, 
 cudaError_t launch_costvol(Tens gwc, Tens cat, Tens vol, int B, int D, cudaStream_t st) {
   const int h = gwc.h, w = gwc.w;
   const size_t smem = (size_t)2 * 8 * (w * 8 + 4) * sizeof(float);
-  if (need_attr(2)) cudaFuncSetAttribute(k_costvol, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  k_costvol<<<dim3(h, B, 4), 256, smem, st>>>(gwc.p, cat.p, vol.p, B, D, h, w);
+  CostvolParams p{gwc.p, cat.p, vol.p, gwc.sample_stride(), gwc.lo_off(), cat.sample_stride(), cat.lo_off(),
+                  vol.sample_stride(), vol.lo_off(), B, D, h, w};
+  if (vol.planes == 2) {
+    if (need_attr(5)) cudaFuncSetAttribute(k_costvol<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    k_costvol<__half><<<dim3(h, B, 4), 256, smem, st>>>(p);
+  } else {
+    if (need_attr(2)) cudaFuncSetAttribute(k_costvol<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    k_costvol<float><<<dim3(h, B, 4), 256, smem, st>>>(p);
+  }
   return cudaGetLastError();
 }
 
@@ -174,8 +197,9 @@ cudaError_t launch_softargmin(Plane cost, Plane disp, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // M5 glue: channel 0 = x2 bilinear upsample of the disparity (align_corners=False), channels 1-3 =
 // left image bilinearly resized to the stage resolution (integer factor f: mean of the central 2x2).
-__global__ void k_refine_in(const float* __restrict__ disp, const float* __restrict__ img, float* __restrict__ out,
-                            int h, int w, int Hf, int Wf, int f) {
+template <typename T>
+__global__ void k_refine_in(const float* __restrict__ disp, const void* __restrict__ img, size_t i_ss, size_t i_lo,
+                            void* __restrict__ out, size_t o_ss, size_t o_lo, int h, int w, int Hf, int Wf, int f) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y, b = blockIdx.z;
   const int H2 = 2 * h, W2 = 2 * w;
@@ -188,31 +212,34 @@ __global__ void k_refine_in(const float* __restrict__ disp, const float* __restr
   const float* dp = disp + (size_t)b * h * w;
   const float up = ly0 * (lx0 * __ldg(dp + y0 * w + x0) + lx1 * __ldg(dp + y0 * w + x1)) +
                    ly1 * (lx0 * __ldg(dp + y1 * w + x0) + lx1 * __ldg(dp + y1 * w + x1));
-  float4 o;
-  o.x = up;
-  const float* ip = img + (size_t)b * Hf * Wf * 8;
+  float o[8] = {up, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const size_t ib = (size_t)b * i_ss;
   if (f == 1) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(ip + ((size_t)y * Wf + x) * 8));
-    o.y = v.x; o.z = v.y; o.w = v.z;
+    float v[8];
+    St<T>::ld8(img, ib + ((size_t)y * Wf + x) * 8, i_lo, v);
+    o[1] = v[0]; o[2] = v[1]; o[3] = v[2];
   } else {
     const int yy = y * f + f / 2 - 1, xx = x * f + f / 2 - 1;
-    const float4 a = __ldg(reinterpret_cast<const float4*>(ip + ((size_t)yy * Wf + xx) * 8));
-    const float4 bq = __ldg(reinterpret_cast<const float4*>(ip + ((size_t)yy * Wf + xx + 1) * 8));
-    const float4 c = __ldg(reinterpret_cast<const float4*>(ip + ((size_t)(yy + 1) * Wf + xx) * 8));
-    const float4 d = __ldg(reinterpret_cast<const float4*>(ip + ((size_t)(yy + 1) * Wf + xx + 1) * 8));
-    o.y = 0.5f * (0.5f * a.x + 0.5f * bq.x) + 0.5f * (0.5f * c.x + 0.5f * d.x);
-    o.z = 0.5f * (0.5f * a.y + 0.5f * bq.y) + 0.5f * (0.5f * c.y + 0.5f * d.y);
-    o.w = 0.5f * (0.5f * a.z + 0.5f * bq.z) + 0.5f * (0.5f * c.z + 0.5f * d.z);
+    float a[8], bq[8], c[8], d[8];
+    St<T>::ld8(img, ib + ((size_t)yy * Wf + xx) * 8, i_lo, a);
+    St<T>::ld8(img, ib + ((size_t)yy * Wf + xx + 1) * 8, i_lo, bq);
+    St<T>::ld8(img, ib + ((size_t)(yy + 1) * Wf + xx) * 8, i_lo, c);
+    St<T>::ld8(img, ib + ((size_t)(yy + 1) * Wf + xx + 1) * 8, i_lo, d);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o[1 + k] = 0.5f * (0.5f * a[k] + 0.5f * bq[k]) + 0.5f * (0.5f * c[k] + 0.5f * d[k]);
   }
-  float4* dst = reinterpret_cast<float4*>(out + (((size_t)b * H2 + y) * W2 + x) * 8);
-  dst[0] = o;
-  dst[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  St<T>::st8(out, (size_t)b * o_ss + ((size_t)y * W2 + x) * 8, o_lo, o);
 }
 
 cudaError_t launch_refine_in(Plane disp, Tens img_full, Tens out, int B, cudaStream_t st) {
   const int f = img_full.h / out.h;
-  k_refine_in<<<dim3(cdiv(out.w, 128), out.h, B), 128, 0, st>>>(disp.p, img_full.p, out.p, disp.h, disp.w,
-                                                               img_full.h, img_full.w, f);
+  const dim3 g(cdiv(out.w, 128), out.h, B);
+  if (out.planes == 2)
+    k_refine_in<__half><<<g, 128, 0, st>>>(disp.p, img_full.p, img_full.sample_stride(), img_full.lo_off(), out.p,
+                                            out.sample_stride(), out.lo_off(), disp.h, disp.w, img_full.h, img_full.w, f);
+  else
+    k_refine_in<float><<<g, 128, 0, st>>>(disp.p, img_full.p, img_full.sample_stride(), img_full.lo_off(), out.p,
+                                           out.sample_stride(), out.lo_off(), disp.h, disp.w, img_full.h, img_full.w, f);
   return cudaGetLastError();
 }
 

@@ -8,6 +8,13 @@ namespace snb {
 cudaError_t launch_conv_direct(ConvParams p, int cout, cudaStream_t st);
 cudaError_t launch_conv_to1(const ConvTo1Params& p, cudaStream_t st);
 
+// k_conv_tc.cu — tcgen05 implicit-GEMM convolution on split-fp16 tensors (M1, M3, M5)
+cudaError_t tc_conv_plan(TcConvPlan* plan, const void* in, int nmax, int cin, int cout, int D, int H, int W, int dil, int kz,
+                         int num_sms);
+cudaError_t launch_conv_tc(const TcConvPlan& plan, int N, const void* w, const float* bias, const void* res, void* out, int relu,
+                           int num_sms, cudaStream_t st);
+void tc_pack_weights(const float* W, int cout, int cin, int kz, int NT, std::vector<__half>& out);
+
 // k_mem.cu — HBM-bound kernels
 // P3 tail on device: s8 NCHW [B,6,H,W] -> C8 [2B][1][Hp][Wp][8] (x/128; left n<B, right n>=B; ch 3..7 = 0)
 cudaError_t launch_pre_s8(const int8_t* s8, Tens img, int B, int H, int W, cudaStream_t st);

@@ -146,8 +146,8 @@ struct Builder {
   bool fail = false;
 
   Tens alloc(int nmul, int ch, int d, int h, int w) {
-    Tens t; t.n = nmul * maxB; t.c = ch; t.cb = (ch + 7) / 8; t.d = d; t.h = h; t.w = w;
-    t.p = static_cast<float*>(c->arena.get(t.bytes()));
+    Tens t; t.n = nmul * maxB; t.c = ch; t.cb = (ch + 7) / 8; t.d = d; t.h = h; t.w = w; t.planes = c->planes;
+    t.p = c->arena.get(t.bytes());
     if (!t.p) fail = true;
     return t;
   }
@@ -162,41 +162,78 @@ struct Builder {
   void tap(const std::string& name, const Tens& t, int nmul) { Stage s; s.t = t; s.nmul = nmul; c->stages[name] = s; }
   void tap(const std::string& name, const Plane& p) { Stage s; s.is_plane = true; s.p = p; c->stages[name] = s; }
 
-  // generic convolution on the fp32 direct path
+  // tcgen05 path: stride-1 3x3 / 3x3x3 convolutions with Cin % 16 == 0 and Cout % 32 == 0
+  bool tc_eligible(const ConvW& cw, int stride) const {
+    return c->planes == 2 && stride == 1 && cw.ks == 3 && cw.cin % 16 == 0 && cw.cout % 32 == 0;
+  }
+
   Tens conv(const std::string& name, const Tens& in, int nmul, int stride, int dil, bool relu, const Tens* res) {
     auto it = c->convs.find(name);
     if (it == c->convs.end()) { fail = true; snprintf(c->err, sizeof(c->err), "no weights for %s", name.c_str()); return Tens(); }
-    const ConvW cw = it->second;
+    ConvW& cw = it->second;
     const int ho = (in.h + stride - 1) / stride, wo = (in.w + stride - 1) / stride;
     Tens out = alloc(nmul, cw.cout, in.d, ho, wo);
+    Op op; op.name = name;
+    const double px = (double)nmul * in.d * ho * wo;
+    op.flops = 2.0 * px * cw.cout * cw.cin * cw.ks * cw.ks * cw.kz;
+    op.bytes = 4.0 * (nmul * (double)in.d * in.h * in.w * in.cb * 8 + px * out.cb * 8 * (res ? 2 : 1));
+    if (tc_eligible(cw, stride)) {
+      TcConvPlan plan;
+      cudaError_t e = tc_conv_plan(&plan, in.p, in.n, cw.cin, cw.cout, in.d, in.h, in.w, dil, cw.kz, c->num_sms);
+      if (e != cudaSuccess) { fail = true; snprintf(c->err, sizeof(c->err), "tc_conv_plan(%s): %s", name.c_str(), cudaGetErrorString(e)); return out; }
+      const int NT = plan.p.NT;
+      if (!cw.w_tc.count(NT)) {
+        std::vector<__half> packed;
+        tc_pack_weights(c->wts[name + ".weight"].data.data(), cw.cout, cw.cin, cw.kz, NT, packed);
+        __half* dw = nullptr;
+        if (cudaMalloc(&dw, packed.size() * sizeof(__half)) != cudaSuccess) { fail = true; return out; }
+        cudaMemcpy(dw, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice);
+        c->wallocs.push_back(dw);
+        cw.w_tc[NT] = dw;
+      }
+      const __half* dw = cw.w_tc[NT];
+      const float* bias = cw.b;
+      const void* rp = res ? res->p : nullptr;
+      void* op_out = out.p;
+      const int sms = c->num_sms, rl = relu ? 1 : 0;
+      op.fn = [plan, nmul, dw, bias, rp, op_out, rl, sms](int B, cudaStream_t st) {
+        return launch_conv_tc(plan, nmul * B, dw, bias, rp, op_out, rl, sms, st);
+      };
+      op.name += " [tc]";
+      ++c->n_tc_convs;
+      c->ops.push_back(op);
+      return out;
+    }
     ConvParams p{};
     p.in = in.p; p.out = out.p; p.w = cw.w; p.bias = cw.b; p.res = res ? res->p : nullptr;
     p.CBin = in.cb; p.Din = in.d; p.Hin = in.h; p.Win = in.w;
     p.CBout = out.cb; p.Dout = out.d; p.Hout = ho; p.Wout = wo;
     p.ks = cw.ks; p.kz = cw.kz; p.stride = stride; p.dil = dil; p.relu = relu ? 1 : 0;
-    Op op; op.name = name;
+    p.in_ss = in.sample_stride(); p.in_lo = in.lo_off(); p.out_ss = out.sample_stride(); p.out_lo = out.lo_off();
+    p.half = c->planes == 2;
     const int cout = cw.cout;
     op.fn = [p, nmul, cout](int B, cudaStream_t st) mutable { ConvParams q = p; q.N = nmul * B; return launch_conv_direct(q, cout, st); };
-    const double px = (double)nmul * in.d * ho * wo;
-    op.flops = 2.0 * px * cw.cout * cw.cin * cw.ks * cw.ks * cw.kz;
-    op.bytes = 4.0 * (nmul * (double)in.d * in.h * in.w * in.cb * 8 + px * out.cb * 8 * (res ? 2 : 1));
+    ++c->n_direct_convs;
     c->ops.push_back(op);
     return out;
   }
 
-  Plane conv_to1(const std::string& name, const Tens& in, int dil, bool relu, const float* res, int res_stride) {
+  Plane conv_to1(const std::string& name, const Tens& in, int dil, bool relu, const Tens* res_c8) {
     auto it = c->convs.find(name);
     if (it == c->convs.end()) { fail = true; snprintf(c->err, sizeof(c->err), "no weights for %s", name.c_str()); return Plane(); }
     const ConvW cw = it->second;
     Plane out = palloc(in.d, in.h, in.w);
     ConvTo1Params p{};
-    p.in = in.p; p.out = out.p; p.w = cw.w; p.bias = cw.b0; p.res = res; p.res_stride = res_stride;
+    p.in = in.p; p.out = out.p; p.w = cw.w; p.bias = cw.b0;
+    p.res = res_c8 ? res_c8->p : nullptr; p.res_c8 = res_c8 ? 1 : 0;
+    if (res_c8) { p.res_ss = res_c8->sample_stride(); p.res_lo = res_c8->lo_off(); }
     p.CBin = in.cb; p.D = in.d; p.H = in.h; p.W = in.w; p.kz = cw.kz; p.dil = dil; p.relu = relu ? 1 : 0;
+    p.in_ss = in.sample_stride(); p.in_lo = in.lo_off(); p.half = c->planes == 2;
     Op op; op.name = name;
     op.fn = [p](int B, cudaStream_t st) { ConvTo1Params q = p; q.N = B; return launch_conv_to1(q, st); };
     const double px = (double)in.d * in.h * in.w;
     op.flops = 2.0 * px * cw.cin * 9 * cw.kz;
-    op.bytes = 4.0 * (px * in.cb * 8 + px * (res ? 2 : 1));
+    op.bytes = 4.0 * (px * in.cb * 8 + px * (res_c8 ? 2 : 1));
     c->ops.push_back(op);
     return out;
   }
@@ -206,6 +243,8 @@ int build_plan(snb_ctx* c) {
   c->ops.clear(); c->stages.clear();
   c->arena.release_all();
   c->arena.reuse = !(c->cfg.flags & SNB_FLAG_KEEP_STAGES);
+  c->planes = c->cfg.precision == SNB_PREC_TC_F16X2 ? 2 : 1;
+  c->n_tc_convs = c->n_direct_convs = 0;
   Builder b{c, c->maxB};
   const int K = c->K, D = c->D, Hp = c->Hp, Wp = c->Wp, h = c->h, w = c->w;
 
@@ -244,15 +283,16 @@ int build_plan(snb_ctx* c) {
   Tens gwc = b.alloc(2, 256, 1, h, w);
   {
     Op op; op.name = "gwc_concat";
-    const size_t half = (size_t)16 * h * w * 8 * sizeof(float);
-    float* dst = gwc.p; const float* s3 = l3.p; const float* s4 = l4.p;
+    // one row per (sample[, hi/lo plane]): 16 blocks from each source into a 32-block row
+    const int planes = c->planes;
+    const size_t half = (size_t)16 * h * w * 8 * (planes == 2 ? sizeof(__half) : sizeof(float));
+    char* dst = static_cast<char*>(gwc.p); const void* s3 = l3.p; const void* s4 = l4.p;
     op.fn = [=](int B, cudaStream_t st) {
-      cudaError_t e = cudaMemcpy2DAsync(dst, 2 * half, s3, half, half, 2 * B, cudaMemcpyDeviceToDevice, st);
+      cudaError_t e = cudaMemcpy2DAsync(dst, 2 * half, s3, half, half, 2 * B * planes, cudaMemcpyDeviceToDevice, st);
       if (e != cudaSuccess) return e;
-      return cudaMemcpy2DAsync(reinterpret_cast<char*>(dst) + half, 2 * half, s4, half, half, 2 * B,
-                               cudaMemcpyDeviceToDevice, st);
+      return cudaMemcpy2DAsync(dst + half, 2 * half, s4, half, half, 2 * B * planes, cudaMemcpyDeviceToDevice, st);
     };
-    op.bytes = 4.0 * half;
+    op.bytes = 4.0 * (double)16 * h * w * 8 * 4;
     c->ops.push_back(op);
   }
   b.free(l3); b.free(l4);
@@ -280,7 +320,7 @@ int build_plan(snb_ctx* c) {
     b.free(v); v = o;
     b.tap("filter" + std::to_string(i), v, 1);
   }
-  Plane cost = b.conv_to1("head.conv3d_alone", v, 1, false, nullptr, 1); b.free(v);
+  Plane cost = b.conv_to1("head.conv3d_alone", v, 1, false, nullptr); b.free(v);
   b.tap("cost", cost);
 
   // ---- M4 soft-argmin ----
@@ -314,7 +354,7 @@ int build_plan(snb_ctx* c) {
       b.free(a); b.free(f); f = o;
     }
     b.tap("refine" + std::to_string(s) + ".feat", f, 1);
-    Plane nd = b.conv_to1(p + ".conv_out", f, 1, true, rin.p, 8);
+    Plane nd = b.conv_to1(p + ".conv_out", f, 1, true, &rin);
     b.free(f); b.free(rin); b.free(disp);
     disp = nd;
     b.tap("disp" + std::to_string(s + 1), disp);

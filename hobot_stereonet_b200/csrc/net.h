@@ -23,6 +23,7 @@ struct HostTensor {
 
 struct ConvW {             // device-resident, kernel-specific packing of one convolution
   float* w = nullptr;      // direct: [cc][cb][kz][tap][8][CO]; to1: [cb][kz][9][8]
+  std::map<int, __half*> w_tc;   // k_conv_tc packing by NT: [cc][k16][dz][ky][hl][kx][2][NT][8]
   float* b = nullptr;      // [cout]
   float b0 = 0.f;          // bias of Cout=1 convs
   int cout = 0, cin = 0, ks = 1, kz = 1;
@@ -63,6 +64,9 @@ struct snb_ctx {
   std::string model_file;
   int H = 0, W = 0, K = 0, D = 0, Hp = 0, Wp = 0, h = 0, w = 0, maxB = 1;
   float qmul = 0.f;
+  int planes = 1;                      // activation storage: 1 fp32, 2 split fp16 (SNB_PREC_TC_F16X2)
+  int num_sms = 148;
+  int n_tc_convs = 0, n_direct_convs = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 
