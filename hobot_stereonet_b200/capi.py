@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsnb200.so")
 
 SNB_OK, SNB_ERR_INVALID, SNB_ERR_MODEL, SNB_ERR_CUDA, SNB_ERR_NOMEM, SNB_ERR_BUSY = 0, -1, -2, -3, -4, -5
 PREC_FP32, PREC_TC_F16X2 = 0, 1
-FLAG_KEEP_STAGES, FLAG_NO_GRAPH, FLAG_CORRECT_CHROMA = 1, 2, 4
+FLAG_KEEP_STAGES, FLAG_NO_GRAPH, FLAG_CORRECT_CHROMA, FLAG_NO_TENSOR = 1, 2, 4, 8
 LAYOUT_NCHW, TENSOR_S8, TENSOR_S32 = 2, 1, 3
 
 
@@ -55,6 +55,8 @@ def load() -> C.CDLL:
         "snb_create": (C.c_int, [C.POINTER(vp), C.POINTER(SnbConfig)]),
         "snb_destroy": (None, [vp]),
         "snb_set_weights": (C.c_int, [vp, vp, u64, C.c_int]),
+        "snb_sys_alloc": (C.c_int, [C.POINTER(vp), u64]),
+        "snb_sys_free": (None, [vp]),
         "snb_get_io": (C.c_int, [vp, C.POINTER(SnbTensorProps), C.POINTER(SnbTensorProps)]),
         "snb_get_model_input_size": (C.c_int, [vp, i32, C.POINTER(i32), C.POINTER(i32)]),
         "snb_infer": (C.c_int, [vp, vp, vp, i32]),

@@ -156,6 +156,31 @@ int snb_set_weights(snb_ctx* c, const void* blob, uint64_t bytes, int is_device)
   return build_plan(c);
 }
 
+// Host tensor memory.  A small header in front of the block records which allocator owns it.
+int snb_sys_alloc(void** ptr, uint64_t bytes) {
+  if (!ptr || !bytes) return SNB_ERR_INVALID;
+  *ptr = nullptr;
+  void* base = nullptr;
+  uint64_t tag = 1;                            // 1: cudaHostAlloc, 2: posix_memalign
+  if (cudaHostAlloc(&base, bytes + 64, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();                        // no device / driver: ordinary host memory
+    if (posix_memalign(&base, 64, bytes + 64) != 0) return SNB_ERR_NOMEM;
+    tag = 2;
+  }
+  memcpy(base, &tag, sizeof(tag));
+  *ptr = static_cast<char*>(base) + 64;
+  return SNB_OK;
+}
+
+void snb_sys_free(void* ptr) {
+  if (!ptr) return;
+  void* base = static_cast<char*>(ptr) - 64;
+  uint64_t tag = 0;
+  memcpy(&tag, base, sizeof(tag));
+  if (tag == 1) cudaFreeHost(base);
+  else if (tag == 2) free(base);
+}
+
 int snb_get_io(const snb_ctx* c, snb_tensor_props* in, snb_tensor_props* out) {
   if (!c) return SNB_ERR_INVALID;
   if (in) {

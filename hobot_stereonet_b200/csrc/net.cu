@@ -164,7 +164,7 @@ struct Builder {
 
   // tcgen05 path: stride-1 3x3 / 3x3x3 convolutions with Cin % 16 == 0 and Cout % 32 == 0
   bool tc_eligible(const ConvW& cw, int stride) const {
-    return c->planes == 2 && stride == 1 && cw.ks == 3 && cw.cin % 16 == 0 && cw.cout % 32 == 0;
+    return c->planes == 2 && !(c->cfg.flags & SNB_FLAG_NO_TENSOR) && stride == 1 && cw.ks == 3 && cw.cin % 16 == 0 && cw.cout % 32 == 0;
   }
 
   Tens conv(const std::string& name, const Tens& in, int nmul, int stride, int dil, bool relu, const Tens* res) {

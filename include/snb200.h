@@ -45,7 +45,8 @@ enum {
 enum {
   SNB_FLAG_KEEP_STAGES = 1,   /* no scratch reuse: every stage tensor stays readable via snb_debug_read */
   SNB_FLAG_NO_GRAPH = 2,      /* launch kernels one by one instead of replaying the captured CUDA graph */
-  SNB_FLAG_CORRECT_CHROMA = 4 /* snb_infer_nv12: de-interleave NV12 chroma properly (NOT the reference behaviour) */
+  SNB_FLAG_CORRECT_CHROMA = 4, /* snb_infer_nv12: de-interleave NV12 chroma properly (NOT the reference behaviour) */
+  SNB_FLAG_NO_TENSOR = 8      /* diagnostics: SNB_PREC_TC_F16X2 storage, but every convolution on the CUDA-core kernel */
 };
 
 /* Replaces dnn_node_para_ptr_->{model_file, model_task_type, task_num} (stereonet_node.cpp:136-144)
@@ -100,6 +101,12 @@ SNB_API int snb_set_weights(snb_ctx* ctx, const void* blob, uint64_t bytes, int 
 /* Seeded synthetic weight blob for refinement-stage count K (the reference's float weights are not
  * recoverable from its BPU binary).  dst == NULL: returns the size needed.  Host-only, no GPU. */
 SNB_API int64_t snb_weights_synthesize(int32_t K, uint64_t seed, void* dst, uint64_t cap);
+
+/* ---- hbSysAllocCachedMem / hbSysFreeMem (preprocess.cpp:956-960,972): host buffers for tensors ----- */
+/* Page-locked host memory when a CUDA device is present (so snb_infer's copies are true async DMA),
+ * plain aligned host memory otherwise.  hbSysFlushMem has no equivalent: nothing to flush. */
+SNB_API int snb_sys_alloc(void** ptr, uint64_t bytes);
+SNB_API void snb_sys_free(void* ptr);
 
 /* ---- hbDNNGet{Input,Output}TensorProperties / GetModelInputSize (stereonet_node.cpp:45,78,94) --- */
 SNB_API int snb_get_io(const snb_ctx* ctx, snb_tensor_props* in, snb_tensor_props* out);

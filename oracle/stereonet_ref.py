@@ -35,20 +35,22 @@ def quant_multiplier(cfg: Config) -> np.float32:
 
 class Oracle:
     def __init__(self, cfg: Config, weights: Dict[str, np.ndarray],
-                 round_fn: Optional[Callable[[torch.Tensor], torch.Tensor]] = None):
+                 round_fn: Optional[Callable[[torch.Tensor, str], torch.Tensor]] = None):
         self.cfg = cfg
         self.w: Tensors = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in weights.items()}
-        # optional operand rounding (e.g. lambda t: t.half().float()) for precision studies
-        self.rf = round_fn or (lambda t: t)
+        # optional operand rounding for precision studies: round_fn(tensor, tag) -> tensor with
+        # tag = "<layer name>:a" (activation operand) / "<layer name>:w" (weight operand) / "costvol",
+        # e.g. lambda t, tag: t.half().float() if tag.startswith("head.refine") else t
+        self.rf = round_fn or (lambda t, name: t)
 
     # -- building blocks -------------------------------------------------------------------
     def conv(self, x, name, stride=1, dil=1, relu=True, add=None):
         w, b = self.w[name + ".weight"], self.w[name + ".bias"]
         pad = dil * (w.shape[-1] // 2)
         if w.dim() == 5:
-            y = F.conv3d(self.rf(x), self.rf(w), b, stride=stride, padding=pad)
+            y = F.conv3d(self.rf(x, name + ":a"), self.rf(w, name + ":w"), b, stride=stride, padding=pad)
         else:
-            y = F.conv2d(self.rf(x), self.rf(w), b, stride=stride, padding=pad, dilation=dil)
+            y = F.conv2d(self.rf(x, name + ":a"), self.rf(w, name + ":w"), b, stride=stride, padding=pad, dilation=dil)
         if add is not None:
             y = y + add
         return F.relu(y) if relu else y
@@ -91,7 +93,7 @@ class Oracle:
         for d in range(min(D, w)):
             vol[:, :CAT_CH, d, :, d:] = cl[:, :, :, d:]
             vol[:, CAT_CH:2 * CAT_CH, d, :, d:] = cr[:, :, :, :w - d]
-            prod = self.rf(gl[:, :, :, d:]) * self.rf(gr[:, :, :, :w - d])
+            prod = self.rf(gl[:, :, :, d:], "costvol") * self.rf(gr[:, :, :, :w - d], "costvol")
             vol[:, 2 * CAT_CH:, d, :, d:] = prod.view(B, GWC_GROUPS, C // GWC_GROUPS, h, w - d).mean(2)
         return vol
 
