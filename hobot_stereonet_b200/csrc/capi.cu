@@ -328,25 +328,33 @@ int64_t snb_debug_read(snb_ctx* c, const char* name, float* dst, uint64_t cap, i
   if (!dst) return (int64_t)n;
   if (cap < n) return SNB_ERR_INVALID;
   const size_t sp = (size_t)t.d * t.h * t.w;
+  const size_t slice = t.slice();
+  const int ws = t.ws(), pad = t.pad;
+  // element (nn, hl, ch, dd, y, x) of the padded C8 layout
+  auto at = [&](int nn, int hl, int ch, int dd, int y, int x) {
+    return ((((size_t)(nn * t.planes + hl) * t.cb + ch / 8) * t.d + dd) * slice) + ((size_t)(y + pad) * ws + x + pad) * 8 + ch % 8;
+  };
   if (t.planes == 2) {
-    std::vector<__half> tmp((size_t)N * 2 * t.cb * sp * 8);
+    std::vector<__half> tmp((size_t)N * 2 * t.cb * t.d * slice);
     CK(c, cudaMemcpy(tmp.data(), t.p, tmp.size() * 2, cudaMemcpyDeviceToHost));
     for (int nn = 0; nn < N; ++nn)
       for (int ch = 0; ch < t.c; ++ch) {
-        const __half* hi = tmp.data() + (((size_t)(nn * 2) * t.cb + ch / 8) * sp) * 8 + ch % 8;
-        const __half* lo = hi + (size_t)t.cb * sp * 8;
         float* d = dst + ((size_t)nn * t.c + ch) * sp;
-        for (size_t i = 0; i < sp; ++i) d[i] = __half2float(hi[i * 8]) + __half2float(lo[i * 8]);
+        for (int dd = 0; dd < t.d; ++dd)
+          for (int y = 0; y < t.h; ++y)
+            for (int x = 0; x < t.w; ++x)
+              d[((size_t)dd * t.h + y) * t.w + x] = __half2float(tmp[at(nn, 0, ch, dd, y, x)]) + __half2float(tmp[at(nn, 1, ch, dd, y, x)]);
       }
     return (int64_t)n;
   }
-  std::vector<float> tmp((size_t)N * t.cb * sp * 8);
+  std::vector<float> tmp((size_t)N * t.cb * t.d * slice);
   CK(c, cudaMemcpy(tmp.data(), t.p, tmp.size() * 4, cudaMemcpyDeviceToHost));
   for (int nn = 0; nn < N; ++nn)
     for (int ch = 0; ch < t.c; ++ch) {
-      const float* src = tmp.data() + (((size_t)nn * t.cb + ch / 8) * sp) * 8 + ch % 8;
       float* d = dst + ((size_t)nn * t.c + ch) * sp;
-      for (size_t i = 0; i < sp; ++i) d[i] = src[i * 8];
+      for (int dd = 0; dd < t.d; ++dd)
+        for (int y = 0; y < t.h; ++y)
+          for (int x = 0; x < t.w; ++x) d[((size_t)dd * t.h + y) * t.w + x] = tmp[at(nn, 0, ch, dd, y, x)];
     }
   return (int64_t)n;
 }

@@ -17,22 +17,47 @@
 namespace snb {
 
 // Two storage types share the C8 indexing:
-//   planes == 1 : fp32                                  [n][cb][d][h][w][8]      (SNB_PREC_FP32)
-//   planes == 2 : split fp16, x = hi + lo, two planes   [n][2][cb][d][h][w][8]   (SNB_PREC_TC_F16X2)
-// Both cost 4 bytes per element.
+//   planes == 1 : fp32                                  [n][cb][d][hs][ws][8]      (SNB_PREC_FP32)
+//   planes == 2 : split fp16, x = hi + lo, two planes   [n][2][cb][d][hs][ws][8]   (SNB_PREC_TC_F16X2)
+// Both cost 4 bytes per element.  Every (cb, d) slice is stored with a zero border of `pad` pixels on all
+// four sides (hs = h + 2*pad, ws = w + 2*pad): kernels write interior pixels only, so a convolution's halo
+// tile is always a run of whole, in-bounds rows (k_conv_tc.cu loads it with plain bulk copies, the zero
+// padding of the convolution is simply there).  Allocations carry TAIL_ROWS rows of slack for the rows a
+// bottom/right tile reads past its slice.
+constexpr int TAIL_ROWS = 18;
 struct Tens {            // C8 activation tensor
   void* p = nullptr;
   int n = 0, cb = 0, d = 1, h = 0, w = 0;
   int c = 0;             // logical channels (<= cb*8)
   int planes = 1;
+  int pad = 0;
+  int hs() const { return h + 2 * pad; }
+  int ws() const { return w + 2 * pad; }
   float* f() const { return static_cast<float*>(p); }
   __half* hp() const { return static_cast<__half*>(p); }
-  size_t plane_elems() const { return (size_t)cb * d * h * w * 8; }       // one (n[,hl]) slab
+  size_t esize() const { return planes == 2 ? 2 : 4; }
+  size_t slice() const { return (size_t)hs() * ws() * 8; }                 // one (cb, d) slice, elements
+  size_t org() const { return ((size_t)pad * ws() + pad) * 8; }            // interior pixel (0,0) inside a slice
+  size_t plane_elems() const { return (size_t)cb * d * slice(); }          // one (n[,hl]) slab
   size_t sample_stride() const { return plane_elems() * planes; }          // elements between samples
   size_t lo_off() const { return planes == 2 ? plane_elems() : 0; }
-  size_t elems() const { return (size_t)n * cb * d * h * w * 8; }
-  size_t bytes() const { return elems() * 4; }
+  size_t elems() const { return (size_t)n * cb * d * slice(); }
+  size_t bytes() const { return elems() * 4 + (size_t)TAIL_ROWS * ws() * 8 * 4; }
 };
+
+// Device view of a C8 tensor: `p` points at interior pixel (0,0) of sample 0, block 0, slice 0, so
+// element(n, cb, d, y, x, e) = p[n*ss + (cb*D + d)*slice + (y*ws + x)*8 + e]  (+ lo for the lo plane).
+struct TV {
+  void* p = nullptr;
+  size_t ss = 0, lo = 0, slice = 0;
+  int ws = 0;
+};
+inline TV view(const Tens& t) {
+  TV v;
+  v.p = static_cast<char*>(t.p) + t.org() * t.esize();
+  v.ss = t.sample_stride(); v.lo = t.lo_off(); v.slice = t.slice(); v.ws = t.ws();
+  return v;
+}
 
 struct Plane {           // dense fp32 [n][d][h][w]
   float* p = nullptr;
@@ -42,41 +67,41 @@ struct Plane {           // dense fp32 [n][d][h][w]
 };
 
 struct ConvParams {
-  const void* in; void* out; const float* w; const float* bias;
-  const void* res;       // residual added before the activation (same layout as out) or nullptr
+  TV in, out, res;       // res: residual added before the activation (same geometry as out) or p == nullptr
+  const float* w; const float* bias;
   int N, CBin, Din, Hin, Win;
   int CBout, Dout, Hout, Wout;
   int ks;                // spatial kernel size 1 or 3
   int kz;                // depth taps 1 (2-D) or 3 (3-D, pad 1)
   int stride, dil, relu;
   int tiles_x;
-  size_t in_ss, in_lo, out_ss, out_lo;   // sample strides / hi->lo plane offsets (elements), see Tens
   int half;              // 0: fp32 storage, 1: split-fp16 storage
 };
 
 struct ConvTo1Params {   // Cout = 1 convolutions (conv3d_alone, refinement conv_out)
-  const void* in; float* out; const float* w; float bias;
-  const void* res; int res_c8;        // residual: fp32 plane (res_c8 = 0) or channel 0 of a C8 tensor of in's storage type
+  TV in;
+  float* out; const float* w; float bias;
+  TV res; int res_c8;    // residual: fp32 plane (res_c8 = 0, res.p = plane) or channel 0 of a C8 tensor of in's storage type
   int N, CBin, D, H, W;
   int kz, dil, relu;
-  size_t in_ss, in_lo;
-  size_t res_ss, res_lo;              // residual C8 tensor: sample stride / hi->lo offset (elements)
   int half;
 };
 
 struct TcConvParams {    // k_conv_tc.cu
-  const __half* w; const float* bias; const __half* res; __half* out;
+  TV in, out, res;       // split-fp16 tensors
+  const __half* w; const float* bias;
   int N, D, H, W, CBin, CBout;
   int dil, kz, relu;
-  int nky;               // kernel rows per pipeline stage: 3 (full halo tile) or 1 (row group, large dilation)
+  int nky;               // kernel rows per pipeline stage: 3 (haloed tile) or 1 (one row group per stage)
+  int contig;            // nky == 3: rows y0-dil .. y0+R-1+dil contiguous (dil < R), else three groups of R rows
   int nk16;              // Cin / 16
   int NT, R;             // output channels / image rows per tile
-  int BW, BH;            // TMA box (pixels)
+  int BW, BH;            // shared-memory tile: pixels per row, rows per stage
   int tiles_x, tiles_y, ccs, total_tiles;
   int nstages;
-  uint32_t a_bytes, w_bytes, tx_bytes;
+  uint32_t a_chunk_bytes, w_bytes, stage_bytes, tx_bytes;
 };
-struct TcConvPlan { CUtensorMap tm_in; TcConvParams p; size_t smem; };
+struct TcConvPlan { TcConvParams p; size_t smem; };
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 

@@ -37,18 +37,18 @@ __global__ void __launch_bounds__(256) k_conv_direct(ConvParams p) {
 
   const int ix0 = tx0 * p.stride - pad, iy0 = ty0 * p.stride - pad;
   const int ntap = p.ks * p.ks;
-  const size_t in_slice = (size_t)p.Hin * p.Win * 8;
+  const size_t in_slice = p.in.slice;
 
   for (int cb = 0; cb < p.CBin; ++cb) {
     for (int kz = 0; kz < p.kz; ++kz) {
       const int zin = dz + kz - (p.kz >> 1);
       if (zin < 0 || zin >= p.Din) continue;          // uniform across the CTA
       __syncthreads();
-      const size_t src = (size_t)n * p.in_ss + ((size_t)cb * p.Din + zin) * in_slice;
+      const size_t src = (size_t)n * p.in.ss + ((size_t)cb * p.Din + zin) * in_slice;
       for (int pix = tid; pix < IH * IW; pix += 256) {
         const int y = iy0 + pix / IW, x = ix0 + pix % IW;
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (y >= 0 && y < p.Hin && x >= 0 && x < p.Win) St<T>::ld8(p.in, src + ((size_t)y * p.Win + x) * 8, p.in_lo, v);
+        if (y >= 0 && y < p.Hin && x >= 0 && x < p.Win) St<T>::ld8(p.in.p, src + ((size_t)y * p.in.ws + x) * 8, p.in.lo, v);
         reinterpret_cast<float4*>(s_in)[2 * pix] = make_float4(v[0], v[1], v[2], v[3]);
         reinterpret_cast<float4*>(s_in)[2 * pix + 1] = make_float4(v[4], v[5], v[6], v[7]);
       }
@@ -102,13 +102,13 @@ __global__ void __launch_bounds__(256) k_conv_direct(ConvParams p) {
       const int idx = i * 64 + half * 32 + lane;
       const int y = ty0 + (idx >> 4), x = tx0 + (idx & 15);
       if (y >= p.Hout || x >= p.Wout) continue;
-      const size_t o = (size_t)n * p.out_ss + ((((size_t)cbo * p.Dout + dz) * p.Hout + y) * p.Wout + x) * 8;
+      const size_t o = (size_t)n * p.out.ss + ((size_t)cbo * p.Dout + dz) * p.out.slice + ((size_t)y * p.out.ws + x) * 8;
       float v[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) v[c] = acc[i][c] + bv[c];
-      if (p.res) {
+      if (p.res.p) {
         float r[8];
-        St<T>::ld8(p.res, o, p.out_lo, r);
+        St<T>::ld8(p.res.p, (size_t)n * p.res.ss + ((size_t)cbo * p.Dout + dz) * p.res.slice + ((size_t)y * p.res.ws + x) * 8, p.res.lo, r);
 #pragma unroll
         for (int c = 0; c < 8; ++c) v[c] += r[c];
       }
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) k_conv_direct(ConvParams p) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) v[c] = fmaxf(v[c], 0.f);
       }
-      St<T>::st8(p.out, o, p.out_lo, v);
+      St<T>::st8(p.out.p, o, p.out.lo, v);
     }
   } else {
     // COT == 4: stage the tile through shared memory as [pixel 256][16 ch], then write whole blocks
@@ -134,13 +134,13 @@ __global__ void __launch_bounds__(256) k_conv_direct(ConvParams p) {
       const int y = ty0 + (idx >> 4), x = tx0 + (idx & 15);
       if (y >= p.Hout || x >= p.Wout) continue;
       const int cbo = (cc * CO >> 3) + blk;
-      const size_t o = (size_t)n * p.out_ss + ((((size_t)cbo * p.Dout + dz) * p.Hout + y) * p.Wout + x) * 8;
+      const size_t o = (size_t)n * p.out.ss + ((size_t)cbo * p.Dout + dz) * p.out.slice + ((size_t)y * p.out.ws + x) * 8;
       float v[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) v[c] = s_o[idx * CO + blk * 8 + c];
-      if (p.res) {
+      if (p.res.p) {
         float r[8];
-        St<T>::ld8(p.res, o, p.out_lo, r);
+        St<T>::ld8(p.res.p, (size_t)n * p.res.ss + ((size_t)cbo * p.Dout + dz) * p.res.slice + ((size_t)y * p.res.ws + x) * 8, p.res.lo, r);
 #pragma unroll
         for (int c = 0; c < 8; ++c) v[c] += r[c];
       }
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256) k_conv_direct(ConvParams p) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) v[c] = fmaxf(v[c], 0.f);
       }
-      St<T>::st8(p.out, o, p.out_lo, v);
+      St<T>::st8(p.out.p, o, p.out.lo, v);
     }
   }
 }
@@ -201,12 +201,12 @@ __global__ void __launch_bounds__(256) k_conv_to1(ConvTo1Params p) {
   const int n = blockIdx.z / p.D, dz = blockIdx.z % p.D;
   if (x >= p.W || y >= p.H) return;
   float acc = p.bias;
-  const size_t slice = (size_t)p.H * p.W * 8;
+  const size_t slice = p.in.slice;
   for (int cb = 0; cb < p.CBin; ++cb) {
     for (int kz = 0; kz < p.kz; ++kz) {
       const int zin = dz + kz - (p.kz >> 1);
       if (zin < 0 || zin >= p.D) continue;
-      const size_t src = (size_t)n * p.in_ss + ((size_t)cb * p.D + zin) * slice;
+      const size_t src = (size_t)n * p.in.ss + ((size_t)cb * p.D + zin) * slice;
       const float* wp = s_w + ((cb * p.kz + kz) * 9) * 8;
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256) k_conv_to1(ConvTo1Params p) {
           const int xx = x + (kx - 1) * p.dil;
           if (xx < 0 || xx >= p.W) continue;
           float v[8];
-          St<T>::ld8(p.in, src + ((size_t)yy * p.W + xx) * 8, p.in_lo, v);
+          St<T>::ld8(p.in.p, src + ((size_t)yy * p.in.ws + xx) * 8, p.in.lo, v);
           const float* w8 = wp + (ky * 3 + kx) * 8;
 #pragma unroll
           for (int c = 0; c < 8; ++c) acc = fmaf(v[c], w8[c], acc);
@@ -226,9 +226,9 @@ __global__ void __launch_bounds__(256) k_conv_to1(ConvTo1Params p) {
     }
   }
   const size_t o = (((size_t)n * p.D + dz) * p.H + y) * p.W + x;
-  if (p.res) {
-    if (p.res_c8) acc += St<T>::ld1(p.res, (size_t)n * p.res_ss + ((size_t)y * p.W + x) * 8, p.res_lo);
-    else acc += __ldg(static_cast<const float*>(p.res) + o);
+  if (p.res.p) {
+    if (p.res_c8) acc += St<T>::ld1(p.res.p, (size_t)n * p.res.ss + ((size_t)y * p.res.ws + x) * 8, p.res.lo);
+    else acc += __ldg(static_cast<const float*>(p.res.p) + o);
   }
   if (p.relu) acc = fmaxf(acc, 0.f);
   p.out[o] = acc;

@@ -11,8 +11,7 @@ namespace snb {
 // s8 NCHW [B,6,H,W] -> C8 image [2B][1][Hp][Wp][8].  Restates the tensor semantics the BPU model
 // gives its input: value = s8 * (1/128) (preprocess.cpp:1037), channels 0-2 left, 3-5 right.
 template <typename T>
-__global__ void k_pre_s8(const int8_t* __restrict__ s8, void* __restrict__ img, size_t ss, size_t lo, int B, int H, int W,
-                         int Hp, int Wp) {
+__global__ void k_pre_s8(const int8_t* __restrict__ s8, TV img, int B, int H, int W, int Hp, int Wp) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int n = blockIdx.z;                  // 0..2B-1
@@ -26,13 +25,13 @@ __global__ void k_pre_s8(const int8_t* __restrict__ s8, void* __restrict__ img, 
     v[1] = (float)src[plane] * 0.0078125f;
     v[2] = (float)src[2 * plane] * 0.0078125f;
   }
-  St<T>::st8(img, (size_t)n * ss + ((size_t)y * Wp + x) * 8, lo, v);
+  St<T>::st8(img.p, (size_t)n * img.ss + ((size_t)y * img.ws + x) * 8, img.lo, v);
 }
 
 cudaError_t launch_pre_s8(const int8_t* s8, Tens img, int B, int H, int W, cudaStream_t st) {
   const dim3 g(cdiv(img.w, 128), img.h, 2 * B);
-  if (img.planes == 2) k_pre_s8<__half><<<g, 128, 0, st>>>(s8, img.p, img.sample_stride(), img.lo_off(), B, H, W, img.h, img.w);
-  else k_pre_s8<float><<<g, 128, 0, st>>>(s8, img.p, img.sample_stride(), img.lo_off(), B, H, W, img.h, img.w);
+  if (img.planes == 2) k_pre_s8<__half><<<g, 128, 0, st>>>(s8, view(img), B, H, W, img.h, img.w);
+  else k_pre_s8<float><<<g, 128, 0, st>>>(s8, view(img), B, H, W, img.h, img.w);
   return cudaGetLastError();
 }
 
@@ -41,8 +40,8 @@ cudaError_t launch_pre_s8(const int8_t* s8, Tens img, int B, int H, int W, cudaS
 // Restates stereonet_node.cpp:702-738 (L/R split), preprocess.h:128-155 (YUV420TOYUV444 incl. the
 // I420-indexing quirk on NV12 data) and preprocess.cpp:1032-1040 (x-128) in one pass.
 template <typename T>
-__global__ void k_pre_nv12(const uint8_t* __restrict__ frames, void* __restrict__ img, size_t ss, size_t lo,
-                           int8_t* __restrict__ s8, int B, int H, int W, int Hp, int Wp, int correct) {
+__global__ void k_pre_nv12(const uint8_t* __restrict__ frames, TV img, int8_t* __restrict__ s8, int B, int H, int W, int Hp,
+                           int Wp, int correct) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int n = blockIdx.z;
@@ -75,16 +74,16 @@ __global__ void k_pre_nv12(const uint8_t* __restrict__ frames, void* __restrict_
       d[0] = sy; d[plane] = su; d[2 * plane] = sv;
     }
   }
-  St<T>::st8(img, (size_t)n * ss + ((size_t)y * Wp + x) * 8, lo, v0);
+  St<T>::st8(img.p, (size_t)n * img.ss + ((size_t)y * img.ws + x) * 8, img.lo, v0);
 }
 
 cudaError_t launch_pre_nv12(const uint8_t* frames, Tens img, int8_t* s8, int B, int H, int W, int correct,
                             cudaStream_t st) {
   const dim3 g(cdiv(img.w, 128), img.h, 2 * B);
   if (img.planes == 2)
-    k_pre_nv12<__half><<<g, 128, 0, st>>>(frames, img.p, img.sample_stride(), img.lo_off(), s8, B, H, W, img.h, img.w, correct);
+    k_pre_nv12<__half><<<g, 128, 0, st>>>(frames, view(img), s8, B, H, W, img.h, img.w, correct);
   else
-    k_pre_nv12<float><<<g, 128, 0, st>>>(frames, img.p, img.sample_stride(), img.lo_off(), s8, B, H, W, img.h, img.w, correct);
+    k_pre_nv12<float><<<g, 128, 0, st>>>(frames, view(img), s8, B, H, W, img.h, img.w, correct);
   return cudaGetLastError();
 }
 
@@ -97,8 +96,7 @@ cudaError_t launch_pre_nv12(const uint8_t* frames, Tens img, int8_t* s8, int B, 
 //                   mean_8( L[g][x][:] * R[g][x-d][:] ), zero where x < d
 // Thread (x, j): consecutive threads write consecutive floats of [x][j] -> fully coalesced stores.
 struct CostvolParams {
-  const void* gwc; const void* cat; void* vol;
-  size_t g_ss, g_lo, c_ss, c_lo, v_ss, v_lo;
+  TV gwc, cat, vol;
   int B, D, h, w;
 };
 
@@ -110,31 +108,30 @@ __global__ void __launch_bounds__(256) k_costvol(CostvolParams p) {
   const int pitch = w * 8 + 4;                                  // +4 floats: 8 blocks hit 8 distinct 16B lanes
   float* sL = sm;                  // [8][pitch]
   float* sR = sm + 8 * pitch;
-  const size_t row = (size_t)w * 8;
   for (int i = threadIdx.x; i < 8 * w; i += blockDim.x) {
     const int j = i / w, x = i % w;
-    const size_t off = (((size_t)(q * 8 + j)) * h + y) * row + (size_t)x * 8;
+    const size_t off = (size_t)(q * 8 + j) * p.gwc.slice + ((size_t)y * p.gwc.ws + x) * 8;
     float v[8];
-    St<T>::ld8(p.gwc, (size_t)b * p.g_ss + off, p.g_lo, v);
+    St<T>::ld8(p.gwc.p, (size_t)b * p.gwc.ss + off, p.gwc.lo, v);
     reinterpret_cast<float4*>(sL + j * pitch + x * 8)[0] = make_float4(v[0], v[1], v[2], v[3]);
     reinterpret_cast<float4*>(sL + j * pitch + x * 8)[1] = make_float4(v[4], v[5], v[6], v[7]);
-    St<T>::ld8(p.gwc, (size_t)(p.B + b) * p.g_ss + off, p.g_lo, v);
+    St<T>::ld8(p.gwc.p, (size_t)(p.B + b) * p.gwc.ss + off, p.gwc.lo, v);
     reinterpret_cast<float4*>(sR + j * pitch + x * 8)[0] = make_float4(v[0], v[1], v[2], v[3]);
     reinterpret_cast<float4*>(sR + j * pitch + x * 8)[1] = make_float4(v[4], v[5], v[6], v[7]);
   }
   __syncthreads();
 
-  const size_t vslice = (size_t)h * w * 8;                      // one (cb, d) slice
-  const size_t vg = (size_t)b * p.v_ss + (size_t)(4 + q) * D * vslice + (size_t)y * row;   // gwc block 4+q
-  const size_t vc = (size_t)b * p.v_ss + (size_t)q * D * vslice + (size_t)y * row;         // concat block q
-  const size_t csrc = (size_t)((q >> 1) ? p.B + b : b) * p.c_ss + ((size_t)(q & 1) * h + y) * row;
+  const size_t vslice = p.vol.slice;                            // one (cb, d) slice
+  const size_t vg = (size_t)b * p.vol.ss + (size_t)(4 + q) * D * vslice + (size_t)y * p.vol.ws * 8;   // gwc block 4+q
+  const size_t vc = (size_t)b * p.vol.ss + (size_t)q * D * vslice + (size_t)y * p.vol.ws * 8;         // concat block q
+  const size_t csrc = (size_t)((q >> 1) ? p.B + b : b) * p.cat.ss + (size_t)(q & 1) * p.cat.slice + (size_t)y * p.cat.ws * 8;
   const bool shifted = (q >> 1) != 0;
 
   for (int e = threadIdx.x; e < w * 8; e += blockDim.x) {
     const int x = e >> 3, j = e & 7;
     const float4 l0 = *reinterpret_cast<const float4*>(sL + j * pitch + x * 8);
     const float4 l1 = *reinterpret_cast<const float4*>(sL + j * pitch + x * 8 + 4);
-    const float cl = St<T>::ld1(p.cat, csrc + e, p.c_lo);      // unshifted concat value (left blocks)
+    const float cl = St<T>::ld1(p.cat.p, csrc + e, p.cat.lo);      // unshifted concat value (left blocks)
     for (int d = 0; d < D; ++d) {
       float g = 0.f, c = 0.f;
       if (x >= d) {
@@ -144,10 +141,10 @@ __global__ void __launch_bounds__(256) k_costvol(CostvolParams p) {
         g = fmaf(l0.y, r0.y, g); g = fmaf(l0.z, r0.z, g); g = fmaf(l0.w, r0.w, g);
         g = fmaf(l1.x, r1.x, g); g = fmaf(l1.y, r1.y, g); g = fmaf(l1.z, r1.z, g); g = fmaf(l1.w, r1.w, g);
         g *= 0.125f;
-        c = shifted ? St<T>::ld1(p.cat, csrc + e - d * 8, p.c_lo) : cl;
+        c = shifted ? St<T>::ld1(p.cat.p, csrc + e - d * 8, p.cat.lo) : cl;
       }
-      St<T>::st1(p.vol, vg + (size_t)d * vslice + e, p.v_lo, g);
-      St<T>::st1(p.vol, vc + (size_t)d * vslice + e, p.v_lo, c);
+      St<T>::st1(p.vol.p, vg + (size_t)d * vslice + e, p.vol.lo, g);
+      St<T>::st1(p.vol.p, vc + (size_t)d * vslice + e, p.vol.lo, c);
     }
   }
 }
@@ -155,8 +152,7 @@ __global__ void __launch_bounds__(256) k_costvol(CostvolParams p) {
 cudaError_t launch_costvol(Tens gwc, Tens cat, Tens vol, int B, int D, cudaStream_t st) {
   const int h = gwc.h, w = gwc.w;
   const size_t smem = (size_t)2 * 8 * (w * 8 + 4) * sizeof(float);
-  CostvolParams p{gwc.p, cat.p, vol.p, gwc.sample_stride(), gwc.lo_off(), cat.sample_stride(), cat.lo_off(),
-                  vol.sample_stride(), vol.lo_off(), B, D, h, w};
+  CostvolParams p{view(gwc), view(cat), view(vol), B, D, h, w};
   if (vol.planes == 2) {
     if (need_attr(5)) cudaFuncSetAttribute(k_costvol<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     k_costvol<__half><<<dim3(h, B, 4), 256, smem, st>>>(p);
@@ -198,11 +194,10 @@ cudaError_t launch_softargmin(Plane cost, Plane disp, cudaStream_t st) {
 // M5 glue: channel 0 = x2 bilinear upsample of the disparity (align_corners=False), channels 1-3 =
 // left image bilinearly resized to the stage resolution (integer factor f: mean of the central 2x2).
 template <typename T>
-__global__ void k_refine_in(const float* __restrict__ disp, const void* __restrict__ img, size_t i_ss, size_t i_lo,
-                            void* __restrict__ out, size_t o_ss, size_t o_lo, int h, int w, int Hf, int Wf, int f) {
+__global__ void k_refine_in(const float* __restrict__ disp, TV img, TV out, int h, int w, int f) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y, b = blockIdx.z;
-  const int H2 = 2 * h, W2 = 2 * w;
+  const int W2 = 2 * w;
   if (x >= W2) return;
   // PyTorch upsample_bilinear2d, scale 0.5: src = max((dst+0.5)*0.5-0.5, 0)
   const float sy = fmaxf((y + 0.5f) * 0.5f - 0.5f, 0.f), sx = fmaxf((x + 0.5f) * 0.5f - 0.5f, 0.f);
@@ -213,33 +208,30 @@ __global__ void k_refine_in(const float* __restrict__ disp, const void* __restri
   const float up = ly0 * (lx0 * __ldg(dp + y0 * w + x0) + lx1 * __ldg(dp + y0 * w + x1)) +
                    ly1 * (lx0 * __ldg(dp + y1 * w + x0) + lx1 * __ldg(dp + y1 * w + x1));
   float o[8] = {up, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const size_t ib = (size_t)b * i_ss;
+  const size_t ib = (size_t)b * img.ss;
+  const int Wf = img.ws;
   if (f == 1) {
     float v[8];
-    St<T>::ld8(img, ib + ((size_t)y * Wf + x) * 8, i_lo, v);
+    St<T>::ld8(img.p, ib + ((size_t)y * Wf + x) * 8, img.lo, v);
     o[1] = v[0]; o[2] = v[1]; o[3] = v[2];
   } else {
     const int yy = y * f + f / 2 - 1, xx = x * f + f / 2 - 1;
     float a[8], bq[8], c[8], d[8];
-    St<T>::ld8(img, ib + ((size_t)yy * Wf + xx) * 8, i_lo, a);
-    St<T>::ld8(img, ib + ((size_t)yy * Wf + xx + 1) * 8, i_lo, bq);
-    St<T>::ld8(img, ib + ((size_t)(yy + 1) * Wf + xx) * 8, i_lo, c);
-    St<T>::ld8(img, ib + ((size_t)(yy + 1) * Wf + xx + 1) * 8, i_lo, d);
+    St<T>::ld8(img.p, ib + ((size_t)yy * Wf + xx) * 8, img.lo, a);
+    St<T>::ld8(img.p, ib + ((size_t)yy * Wf + xx + 1) * 8, img.lo, bq);
+    St<T>::ld8(img.p, ib + ((size_t)(yy + 1) * Wf + xx) * 8, img.lo, c);
+    St<T>::ld8(img.p, ib + ((size_t)(yy + 1) * Wf + xx + 1) * 8, img.lo, d);
 #pragma unroll
     for (int k = 0; k < 3; ++k) o[1 + k] = 0.5f * (0.5f * a[k] + 0.5f * bq[k]) + 0.5f * (0.5f * c[k] + 0.5f * d[k]);
   }
-  St<T>::st8(out, (size_t)b * o_ss + ((size_t)y * W2 + x) * 8, o_lo, o);
+  St<T>::st8(out.p, (size_t)b * out.ss + ((size_t)y * out.ws + x) * 8, out.lo, o);
 }
 
 cudaError_t launch_refine_in(Plane disp, Tens img_full, Tens out, int B, cudaStream_t st) {
   const int f = img_full.h / out.h;
   const dim3 g(cdiv(out.w, 128), out.h, B);
-  if (out.planes == 2)
-    k_refine_in<__half><<<g, 128, 0, st>>>(disp.p, img_full.p, img_full.sample_stride(), img_full.lo_off(), out.p,
-                                            out.sample_stride(), out.lo_off(), disp.h, disp.w, img_full.h, img_full.w, f);
-  else
-    k_refine_in<float><<<g, 128, 0, st>>>(disp.p, img_full.p, img_full.sample_stride(), img_full.lo_off(), out.p,
-                                           out.sample_stride(), out.lo_off(), disp.h, disp.w, img_full.h, img_full.w, f);
+  if (out.planes == 2) k_refine_in<__half><<<g, 128, 0, st>>>(disp.p, view(img_full), view(out), disp.h, disp.w, f);
+  else k_refine_in<float><<<g, 128, 0, st>>>(disp.p, view(img_full), view(out), disp.h, disp.w, f);
   return cudaGetLastError();
 }
 

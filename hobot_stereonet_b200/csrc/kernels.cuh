@@ -9,9 +9,8 @@ cudaError_t launch_conv_direct(ConvParams p, int cout, cudaStream_t st);
 cudaError_t launch_conv_to1(const ConvTo1Params& p, cudaStream_t st);
 
 // k_conv_tc.cu — tcgen05 implicit-GEMM convolution on split-fp16 tensors (M1, M3, M5)
-cudaError_t tc_conv_plan(TcConvPlan* plan, const void* in, int nmax, int cin, int cout, int D, int H, int W, int dil, int kz,
-                         int num_sms);
-cudaError_t launch_conv_tc(const TcConvPlan& plan, int N, const void* w, const float* bias, const void* res, void* out, int relu,
+cudaError_t tc_conv_plan(TcConvPlan* plan, const Tens& in, const Tens& out, int cin, int cout, int dil, int kz, int num_sms);
+cudaError_t launch_conv_tc(const TcConvPlan& plan, int N, const void* w, const float* bias, const Tens* res, int relu,
                            int num_sms, cudaStream_t st);
 void tc_pack_weights(const float* W, int cout, int cin, int kz, int NT, std::vector<__half>& out);
 

@@ -14,6 +14,8 @@ namespace snb {
 static const int LAYER_BLOCKS[4] = {3, 16, 3, 3};
 static const int LAYER_CH[4] = {32, 64, 128, 128};
 static const int REF_DIL[6] = {1, 2, 4, 8, 1, 1};
+// zero border (pixels) of the padded C8 layout: >= the largest dilation of any tcgen05 consumer
+static const int PAD_BACKBONE = 2, PAD_REFINE = 8;
 
 // ---- weight blob ("SNB2WGT1", oracle/weights.py documents the layout) -----------------------------
 int parse_blob(snb_ctx* c, const void* blob, size_t bytes) {
@@ -115,18 +117,18 @@ int upload_weights(snb_ctx* c) {
 }
 
 // ---- scratch arena: stream-ordered reuse of activation buffers -----------------------------------
-void* Arena::get(size_t bytes) {
+// A block is only ever reused by a tensor of identical geometry (`key`): the zero borders of the padded
+// C8 layout are written once, here, and every kernel writes interior pixels only.
+void* Arena::get(size_t bytes, uint64_t key) {
   bytes = (bytes + 255) / 256 * 256;
   if (reuse) {
-    int best = -1;
-    for (int i = 0; i < (int)blks.size(); ++i)
-      if (blks[i].free && blks[i].bytes >= bytes && (best < 0 || blks[i].bytes < blks[best].bytes)) best = i;
-    if (best >= 0 && blks[best].bytes <= bytes * 2) { blks[best].free = false; return blks[best].p; }
+    for (auto& b : blks)
+      if (b.free && b.key == key && b.bytes == bytes) { b.free = false; return b.p; }
   }
   void* p = nullptr;
   if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
   cudaMemset(p, 0, bytes);
-  blks.push_back({p, bytes, false});
+  blks.push_back({p, bytes, false, key});
   total += bytes;
   return p;
 }
@@ -145,15 +147,16 @@ struct Builder {
   int maxB;
   bool fail = false;
 
-  Tens alloc(int nmul, int ch, int d, int h, int w) {
-    Tens t; t.n = nmul * maxB; t.c = ch; t.cb = (ch + 7) / 8; t.d = d; t.h = h; t.w = w; t.planes = c->planes;
-    t.p = c->arena.get(t.bytes());
+  Tens alloc(int nmul, int ch, int d, int h, int w, int pad) {
+    Tens t; t.n = nmul * maxB; t.c = ch; t.cb = (ch + 7) / 8; t.d = d; t.h = h; t.w = w; t.planes = c->planes; t.pad = pad;
+    const uint64_t key = ((((uint64_t)t.n * 64 + t.cb) * 1024 + t.d) * 8192 + t.h) * 8192 + t.w + ((uint64_t)pad << 58);
+    t.p = c->arena.get(t.bytes(), key);
     if (!t.p) fail = true;
     return t;
   }
   Plane palloc(int d, int h, int w) {
     Plane p; p.n = maxB; p.d = d; p.h = h; p.w = w;
-    p.p = static_cast<float*>(c->arena.get(p.bytes()));
+    p.p = static_cast<float*>(c->arena.get(p.bytes(), ~(uint64_t)0));
     if (!p.p) fail = true;
     return p;
   }
@@ -172,14 +175,14 @@ struct Builder {
     if (it == c->convs.end()) { fail = true; snprintf(c->err, sizeof(c->err), "no weights for %s", name.c_str()); return Tens(); }
     ConvW& cw = it->second;
     const int ho = (in.h + stride - 1) / stride, wo = (in.w + stride - 1) / stride;
-    Tens out = alloc(nmul, cw.cout, in.d, ho, wo);
+    Tens out = alloc(nmul, cw.cout, in.d, ho, wo, in.pad);
     Op op; op.name = name;
     const double px = (double)nmul * in.d * ho * wo;
     op.flops = 2.0 * px * cw.cout * cw.cin * cw.ks * cw.ks * cw.kz;
     op.bytes = 4.0 * (nmul * (double)in.d * in.h * in.w * in.cb * 8 + px * out.cb * 8 * (res ? 2 : 1));
-    if (tc_eligible(cw, stride)) {
+    if (tc_eligible(cw, stride) && in.pad >= dil) {
       TcConvPlan plan;
-      cudaError_t e = tc_conv_plan(&plan, in.p, in.n, cw.cin, cw.cout, in.d, in.h, in.w, dil, cw.kz, c->num_sms);
+      cudaError_t e = tc_conv_plan(&plan, in, out, cw.cin, cw.cout, dil, cw.kz, c->num_sms);
       if (e != cudaSuccess) { fail = true; snprintf(c->err, sizeof(c->err), "tc_conv_plan(%s): %s", name.c_str(), cudaGetErrorString(e)); return out; }
       const int NT = plan.p.NT;
       if (!cw.w_tc.count(NT)) {
@@ -193,11 +196,11 @@ struct Builder {
       }
       const __half* dw = cw.w_tc[NT];
       const float* bias = cw.b;
-      const void* rp = res ? res->p : nullptr;
-      void* op_out = out.p;
+      const bool has_res = res != nullptr;
+      const Tens rt = res ? *res : Tens();
       const int sms = c->num_sms, rl = relu ? 1 : 0;
-      op.fn = [plan, nmul, dw, bias, rp, op_out, rl, sms](int B, cudaStream_t st) {
-        return launch_conv_tc(plan, nmul * B, dw, bias, rp, op_out, rl, sms, st);
+      op.fn = [plan, nmul, dw, bias, has_res, rt, rl, sms](int B, cudaStream_t st) {
+        return launch_conv_tc(plan, nmul * B, dw, bias, has_res ? &rt : nullptr, rl, sms, st);
       };
       op.name += " [tc]";
       ++c->n_tc_convs;
@@ -205,11 +208,11 @@ struct Builder {
       return out;
     }
     ConvParams p{};
-    p.in = in.p; p.out = out.p; p.w = cw.w; p.bias = cw.b; p.res = res ? res->p : nullptr;
+    p.in = view(in); p.out = view(out); p.w = cw.w; p.bias = cw.b;
+    if (res) p.res = view(*res);
     p.CBin = in.cb; p.Din = in.d; p.Hin = in.h; p.Win = in.w;
     p.CBout = out.cb; p.Dout = out.d; p.Hout = ho; p.Wout = wo;
     p.ks = cw.ks; p.kz = cw.kz; p.stride = stride; p.dil = dil; p.relu = relu ? 1 : 0;
-    p.in_ss = in.sample_stride(); p.in_lo = in.lo_off(); p.out_ss = out.sample_stride(); p.out_lo = out.lo_off();
     p.half = c->planes == 2;
     const int cout = cw.cout;
     op.fn = [p, nmul, cout](int B, cudaStream_t st) mutable { ConvParams q = p; q.N = nmul * B; return launch_conv_direct(q, cout, st); };
@@ -224,11 +227,11 @@ struct Builder {
     const ConvW cw = it->second;
     Plane out = palloc(in.d, in.h, in.w);
     ConvTo1Params p{};
-    p.in = in.p; p.out = out.p; p.w = cw.w; p.bias = cw.b0;
-    p.res = res_c8 ? res_c8->p : nullptr; p.res_c8 = res_c8 ? 1 : 0;
-    if (res_c8) { p.res_ss = res_c8->sample_stride(); p.res_lo = res_c8->lo_off(); }
+    p.in = view(in); p.out = out.p; p.w = cw.w; p.bias = cw.b0;
+    p.res_c8 = res_c8 ? 1 : 0;
+    if (res_c8) p.res = view(*res_c8);
     p.CBin = in.cb; p.D = in.d; p.H = in.h; p.W = in.w; p.kz = cw.kz; p.dil = dil; p.relu = relu ? 1 : 0;
-    p.in_ss = in.sample_stride(); p.in_lo = in.lo_off(); p.half = c->planes == 2;
+    p.half = c->planes == 2;
     Op op; op.name = name;
     op.fn = [p](int B, cudaStream_t st) { ConvTo1Params q = p; q.N = B; return launch_conv_to1(q, st); };
     const double px = (double)in.d * in.h * in.w;
@@ -249,7 +252,7 @@ int build_plan(snb_ctx* c) {
   const int K = c->K, D = c->D, Hp = c->Hp, Wp = c->Wp, h = c->h, w = c->w;
 
   // input image, C8 [2B][1][Hp][Wp][8]; the pre-process op is issued by the caller (s8 or NV12 source)
-  c->img = b.alloc(2, 3, 1, Hp, Wp);
+  c->img = b.alloc(2, 3, 1, Hp, Wp, PAD_BACKBONE);
   Tens img = c->img;
   b.tap("img", img, 2);
 
@@ -280,12 +283,12 @@ int build_plan(snb_ctx* c) {
   }
   (void)LAYER_CH;
   // gwc feature = cat(layer3, layer4) along channels: [2B][32][h][w][8]
-  Tens gwc = b.alloc(2, 256, 1, h, w);
+  Tens gwc = b.alloc(2, 256, 1, h, w, PAD_BACKBONE);
   {
     Op op; op.name = "gwc_concat";
     // one row per (sample[, hi/lo plane]): 16 blocks from each source into a 32-block row
     const int planes = c->planes;
-    const size_t half = (size_t)16 * h * w * 8 * (planes == 2 ? sizeof(__half) : sizeof(float));
+    const size_t half = 16 * l3.slice() * l3.esize();     // 16 channel blocks incl. their zero borders
     char* dst = static_cast<char*>(gwc.p); const void* s3 = l3.p; const void* s4 = l4.p;
     op.fn = [=](int B, cudaStream_t st) {
       cudaError_t e = cudaMemcpy2DAsync(dst, 2 * half, s3, half, half, 2 * B * planes, cudaMemcpyDeviceToDevice, st);
@@ -302,7 +305,7 @@ int build_plan(snb_ctx* c) {
   b.tap("cat", cat, 2);
 
   // ---- M2 cost volume [B][8][D][h][w][8] ----
-  Tens vol = b.alloc(1, 64, D, h, w);
+  Tens vol = b.alloc(1, 64, D, h, w, PAD_BACKBONE);
   {
     Op op; op.name = "costvol";
     op.fn = [=](int B, cudaStream_t st) { return launch_costvol(gwc, cat, vol, B, D, st); };
@@ -338,7 +341,7 @@ int build_plan(snb_ctx* c) {
   for (int s = 0; s < K; ++s) {
     const std::string p = "head.refine." + std::to_string(s);
     const int hs = disp.h * 2, ws = disp.w * 2;
-    Tens rin = b.alloc(1, 4, 1, hs, ws);
+    Tens rin = b.alloc(1, 4, 1, hs, ws, PAD_REFINE);
     {
       Op op; op.name = p + ".in";
       Plane dsrc = disp;

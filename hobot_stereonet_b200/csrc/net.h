@@ -44,11 +44,11 @@ struct Stage {             // named tap for snb_debug_read
 };
 
 struct Arena {
-  struct Blk { void* p; size_t bytes; bool free; };
+  struct Blk { void* p; size_t bytes; bool free; uint64_t key; };
   std::vector<Blk> blks;
   bool reuse = true;
   size_t total = 0;
-  void* get(size_t bytes);
+  void* get(size_t bytes, uint64_t key);
   void put(void* p);
   void release_all();
 };
