@@ -92,14 +92,15 @@ struct TcConvParams {    // k_conv_tc.cu
   const __half* w; const float* bias;
   int N, D, H, W, CBin, CBout;
   int dil, kz, relu;
-  int nky;               // kernel rows per pipeline stage: 3 (haloed tile) or 1 (one row group per stage)
-  int contig;            // nky == 3: rows y0-dil .. y0+R-1+dil contiguous (dil < R), else three groups of R rows
   int nk16;              // Cin / 16
-  int NT, R;             // output channels / image rows per tile
-  int BW, BH;            // shared-memory tile: pixels per row, rows per stage
+  int R;                 // output rows per tile (template instance)
+  int BW, BH;            // shared-memory tile: pixels per row, input rows per stage (R + 2)
+  int in_pad;            // zero border of the input tensor (rows below H + in_pad are never read)
   int tiles_x, tiles_y, ccs, total_tiles;
   int nstages;
-  uint32_t a_chunk_bytes, w_bytes, stage_bytes, tx_bytes;
+  uint32_t a_chunk_bytes, w_bytes, stage_bytes;
+  long long* prof;       // SNB_TC_PROF=1: per-CTA cycle counters of each pipeline role (16 per CTA)
+  int dbg;               // timing experiments only (env SNB_TC_DEBUG): 1 no loads, 2 no MMAs, 4 no global stores
 };
 struct TcConvPlan { TcConvParams p; size_t smem; };
 

@@ -1,29 +1,37 @@
 // tcgen05 implicit-GEMM convolution (SNB_PREC_TC_F16X2): stride-1 3x3 (any dilation) and 3x3x3
 // convolutions as shifted-window GEMMs on the 5th-gen tensor cores, with fp32-class accuracy.
 //
-//   GEMM view      M = 128 consecutive pixels of one image row, N = output channels, K = 16 input channels
-//                  per tcgen05.mma (kind::f16, fp32 accumulate in TMEM).
-//   operands       activations and weights are split fp16 (x = hi + lo).  Per (filter tap, 16 channels, row):
-//                    MMA1  A_hi x [W_hi | W_lo]   N = 2*NT  -> TMEM columns [main | corr]
-//                    MMA2  A_lo x  W_hi           N =   NT  -> accumulates into corr
-//                  (lo*lo ~ 2^-22 is dropped).  Stacking W_hi|W_lo along N halves the shared-memory operand
-//                  reads of the activation tile, which bound small-N MMAs (4 KB of A per 128x16 tile).
-//   accumulation   the tensor core adds into TMEM with truncation, which biases long chains (measured
-//                  -6e-6 relative over 27*Cin/16 steps: 1.4e-3 px end-point error).  So a TMEM chain
-//                  covers only the 9 taps of one 16-channel chunk; the epilogue warps drain every chain
-//                  with tcgen05.ld and accumulate across chunks in fp32 registers (round-to-nearest), the
-//                  large hi*hi sum and the small correction sum kept apart until then.
-//   A staging      activations live in HBM with a zero border (common.cuh), so the haloed pixel tile of a
-//                  stage is whole rows: one cp.async.bulk per (plane, 8-channel chunk, row) lands it in the
-//                  no-swizzle K-major core-matrix layout [plane][chunk][row][pixel][8ch]; every filter tap
-//                  is a different start address of the same tile (pixel shift = 16 B), so the 9 taps
-//                  re-read shared memory, not L2.
-//   pipeline       warp 0: bulk-copy producer (all lanes issue), warp 1: MMA issuer (one lane), warp 2:
-//                  TMEM allocator, warps 4-11: epilogue (two warps per TMEM lane quadrant, half the
-//                  columns each).  smem ring of `nstages` stages (full/empty mbarriers); TMEM is a ring of
-//                  512/(2*NT) row slots (row_full/row_empty) so draining row r overlaps the MMAs of the
-//                  following rows.  Persistent: grid = min(tiles, #SM).
+//   GEMM view      M = 128 consecutive pixels of one INPUT row, K = 16 input channels per tcgen05.mma
+//                  (kind::f16, fp32 accumulate in TMEM), N = the 32 output channels of the tile stacked over
+//                  the three kernel rows ky and over the hi/lo halves of the weights:
+//                    MMA1  A_hi x [W_hi(ky0..2) | W_lo(ky0..2)]   N = 192  -> TMEM columns [main | corr]
+//                    MMA2  A_lo x  W_hi(ky0..2)                   N =  96  -> accumulates into corr
+//                  Input row j therefore yields, in one pass over its pixels, its contribution to output rows
+//                  j, j-1 and j-2 of the tile; the kernel column kx is a 16-byte shift of the A start address.
+//                  Measured on B200 (tools/ubench): one M=128 MMA costs max(N/2, 32 + N/4) cycles - the 4 KB
+//                  A tile is re-read from shared memory by every MMA - so wide N is what fills the tensor
+//                  pipe: 96 + 56 cycles per (row, kx, 16 ch) here against 9 x 88 for per-tap N = 64/32 MMAs.
+//   operands       activations and weights are split fp16 (x = hi + lo); hi*hi lands in `main`, hi*lo + lo*hi
+//                  in `corr`, lo*lo (2^-22) is dropped.
+//   accumulation   the tensor core adds into TMEM with truncation, which biases long chains (1.4e-3 px
+//                  end-point error when all 27*Cin/16 steps shared one accumulator).  A TMEM chain here is
+//                  the 3 kx taps of one 16-channel chunk; the epilogue warps drain every chain with
+//                  tcgen05.ld and accumulate in fp32 registers (round to nearest).
+//   tile           128 pixels x R output rows x 32 channels.  Rows of a tile are `dil` apart (a comb), so
+//                  the vertical taps always hit the R + 2 input rows of the same comb, whatever the dilation.
+//   A staging      activations live in HBM with a zero border (common.cuh), so a stage's input rows are whole
+//                  in-bounds runs: one cp.async.bulk per (plane, 8-channel chunk, row) lands them in the
+//                  no-swizzle K-major core-matrix layout [plane][chunk][row][pixel][8ch].
+//   pipeline       warp 0: bulk-copy producer (all lanes issue), warp 1: MMA issuer (warp-uniform control,
+//                  one elected lane issues), warp 2: TMEM allocator, warps 4-11: epilogue (two warps per TMEM
+//                  lane quadrant, 16 channels each).  smem ring of `nstages` stages (full/empty mbarriers);
+//                  TMEM holds two 192-column row slots (slot_full/slot_empty) so draining input row j overlaps
+//                  the MMAs of row j+1.  Persistent: grid = min(tiles, #SM).
 // Covers SURVEY.md §8a rows M1 (backbone), M3 (3-D aggregation), M5 (refinement blocks).
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_ptx.cuh"
@@ -34,25 +42,40 @@ using namespace ptx;
 
 constexpr int TC_THREADS = 384;
 constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_NT = 32;                    // output channels per tile
+constexpr int TC_SLOT_COLS = 6 * TC_NT;      // 192: [main ky0..2 | corr ky0..2], ordered [half][ky][16 ch]
+constexpr uint32_t TC_W_BYTES = 3 * 2 * TC_SLOT_COLS * 16;   // one stage of weights: [kx][chunk][192 rows][8 halfs]
 
-template <int NT, int R>
+struct TileCoord { int cc, tx, d, n, ybase; };
+
+__device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int t, int R) {
+  TileCoord c;
+  c.cc = t % p.ccs; t /= p.ccs;
+  c.tx = t % p.tiles_x; t /= p.tiles_x;
+  const int ty = t % p.tiles_y; t /= p.tiles_y;
+  c.d = t % p.D; c.n = t / p.D;
+  c.ybase = (ty / p.dil) * (R * p.dil) + ty % p.dil;      // first output row of the comb
+  return c;
+}
+
+template <int R>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcConvParams p) {
-  constexpr int S = 512 / (2 * NT);          // TMEM row slots
-  constexpr int CW = NT / 2;                 // output channels per epilogue thread
+  constexpr int BH = R + 2;                  // input rows per stage
+  constexpr int NT = TC_NT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.nstages * p.stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + p.nstages;
-  uint64_t* row_full = bars + 2 * p.nstages;
-  uint64_t* row_empty = row_full + S;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(row_empty + S);
+  uint64_t* slot_full = bars + 2 * p.nstages;
+  uint64_t* slot_empty = slot_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slot_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.nstages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < S; ++i) { mbar_init(&row_full[i], 1); mbar_init(&row_empty[i], TC_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&slot_full[i], 1); mbar_init(&slot_empty[i], TC_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -60,163 +83,164 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcConvParams p)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
-  const int kgroups = 3 / p.nky;            // stages per (k16, dz): 1 (haloed tile) or 3 (one kernel row each)
   const int zpad = p.kz >> 1;
-  const uint32_t a_plane = 2 * p.a_chunk_bytes;          // hi plane -> lo plane inside a stage
 
   if (warp == 0) {
     // ================================ bulk-copy producer ================================
     const __half* in = static_cast<const __half*>(p.in.p);
+    const uint32_t row_bytes = (uint32_t)p.BW * 16;
     uint32_t it = 0;
+    long long w_empty = 0, t_start = clock64();
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      int q = t;
-      const int cc = q % p.ccs; q /= p.ccs;
-      const int tx = q % p.tiles_x; q /= p.tiles_x;
-      const int ty = q % p.tiles_y; q /= p.tiles_y;
-      const int d = q % p.D, n = q / p.D;
-      const int x0 = tx * 128, y0 = ty * R;
+      const TileCoord tc = decode_tile(p, t, R);
+      const int x0 = tc.tx * 128, y0 = tc.ybase - p.dil;           // first input row
+      // rows at or below H + pad feed masked outputs only: skip them (keeps every copy inside the slice)
+      int nrows = (p.H + p.in_pad - 1 - y0) / p.dil + 1;
+      nrows = nrows > BH ? BH : nrows;
+      for (int k16 = 0; k16 < p.nk16; ++k16) {
+        for (int dz = 0; dz < p.kz; ++dz) {
+          const int zin = tc.d + dz - zpad;
+          if (zin < 0 || zin >= p.D) continue;
+          const int slot = it % p.nstages;
+          uint8_t* sa = smem + (size_t)slot * p.stage_bytes;
+          if (lane == 0) {
+            const long long c0 = clock64();
+            mbar_wait(&empty[slot], ((it / p.nstages) & 1) ^ 1);
+            w_empty += clock64() - c0;
+            mbar_expect_tx(&full[slot], (p.dbg & 1) ? 0u : 4u * nrows * row_bytes + TC_W_BYTES);
+          }
+          __syncwarp();
+          ++it;
+          if (p.dbg & 1) continue;
+          for (int i = lane; i < 4 * BH; i += 32) {
+            const int pc = i / BH, j = i - pc * BH;          // pc = plane*2 + chunk
+            if (j >= nrows) continue;
+            const int y = y0 + j * p.dil;
+            const __half* src = in + (size_t)tc.n * p.in.ss + (size_t)(pc >> 1) * p.in.lo +
+                                ((size_t)(k16 * 2 + (pc & 1)) * p.D + zin) * p.in.slice +
+                                ((ptrdiff_t)y * p.in.ws + (x0 - p.dil)) * 8;
+            bulk_load(sa + (size_t)pc * p.a_chunk_bytes + (size_t)j * row_bytes, src, row_bytes, &full[slot]);
+          }
+          if (lane == 0) {
+            const __half* wsrc = p.w + (((size_t)tc.cc * p.nk16 + k16) * p.kz + dz) * (size_t)(TC_W_BYTES / 2);
+            bulk_load(sa + 4 * (size_t)p.a_chunk_bytes, wsrc, TC_W_BYTES, &full[slot]);
+          }
+        }
+      }
+    }
+    if (p.prof && lane == 0) { p.prof[blockIdx.x * 16 + 0] = clock64() - t_start; p.prof[blockIdx.x * 16 + 1] = w_empty; p.prof[blockIdx.x * 16 + 2] = it; }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    // Control flow is warp-uniform; only the elected lane executes tcgen05.mma / commit, so the compiler
+    // emits straight-line UTCHMMA with uniform-register descriptor arithmetic.
+    const bool leader = elect_one();
+    const uint32_t idesc1 = make_idesc_f16(128, TC_SLOT_COLS), idesc2 = make_idesc_f16(128, TC_SLOT_COLS / 2);
+    const uint32_t a_lbo = p.a_chunk_bytes, b_lbo = (uint32_t)(TC_SLOT_COLS * 16);
+    const uint32_t row16 = (uint32_t)p.BW, dil16 = (uint32_t)p.dil;          // descriptor address units of 16 B
+    uint32_t it = 0, rs = 0;
+    long long w_full = 0, w_slot = 0, t_start = clock64();
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const int d = (t / (p.ccs * p.tiles_x * p.tiles_y)) % p.D;
       for (int k16 = 0; k16 < p.nk16; ++k16) {
         for (int dz = 0; dz < p.kz; ++dz) {
           const int zin = d + dz - zpad;
           if (zin < 0 || zin >= p.D) continue;
-          for (int g = 0; g < kgroups; ++g, ++it) {
-            const int slot = it % p.nstages;
-            uint8_t* sa = smem + (size_t)slot * p.stage_bytes;
-            if (lane == 0) {
-              mbar_wait(&empty[slot], ((it / p.nstages) & 1) ^ 1);
-              mbar_expect_tx(&full[slot], p.tx_bytes);
+          const int slot = it % p.nstages;
+          { const long long c0 = clock64(); mbar_wait(&full[slot], (it / p.nstages) & 1); w_full += clock64() - c0; }
+          ++it;
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)slot * p.stage_bytes);
+          const uint64_t da_hi = make_smem_desc(sa, a_lbo, 128);
+          const uint64_t da_lo = make_smem_desc(sa + 2 * p.a_chunk_bytes, a_lbo, 128);
+          const uint64_t db = make_smem_desc(sa + 4 * p.a_chunk_bytes, b_lbo, 128);
+          constexpr uint32_t KX_B = 2 * TC_SLOT_COLS;                // 16-byte units between the kx weight blocks
+#pragma unroll
+          for (int j = 0; j < BH; ++j, ++rs) {
+            const uint32_t ts = rs & 1;
+            { const long long c0 = clock64(); mbar_wait(&slot_empty[ts], ((rs >> 1) & 1) ^ 1); w_slot += clock64() - c0; }
+            tc_fence_after();
+            if (leader) {
+              const uint32_t dcol = tmem_base + ts * TC_SLOT_COLS;
+              const uint64_t a_hi = da_hi + (uint64_t)(j * row16), a_lo = da_lo + (uint64_t)(j * row16);
+              if (!(p.dbg & 2)) {
+                umma_f16_zero(dcol, a_hi, db, idesc1);
+                umma_f16_acc(dcol + TC_SLOT_COLS / 2, a_lo, db, idesc2);
+                umma_f16_acc(dcol, a_hi + dil16, db + KX_B, idesc1);
+                umma_f16_acc(dcol + TC_SLOT_COLS / 2, a_lo + dil16, db + KX_B, idesc2);
+                umma_f16_acc(dcol, a_hi + 2 * dil16, db + 2 * KX_B, idesc1);
+                umma_f16_acc(dcol + TC_SLOT_COLS / 2, a_lo + 2 * dil16, db + 2 * KX_B, idesc2);
+              }
+              umma_commit(&slot_full[ts]);       // this input row's chain is complete once these MMAs retire
             }
             __syncwarp();
-            const uint32_t row_bytes = (uint32_t)p.BW * 16;
-            for (int i = lane; i < 4 * p.BH; i += 32) {
-              const int pc = i / p.BH, j = i - pc * p.BH;          // pc = plane*2 + chunk
-              int y;
-              if (p.nky == 1) y = y0 + (g - 1) * p.dil + j;
-              else if (p.contig) y = y0 - p.dil + j;
-              else y = y0 + (j / R - 1) * p.dil + (j % R);
-              const __half* src = in + (size_t)n * p.in.ss + (size_t)(pc >> 1) * p.in.lo +
-                                  ((size_t)(k16 * 2 + (pc & 1)) * p.D + zin) * p.in.slice +
-                                  ((ptrdiff_t)y * p.in.ws + (x0 - p.dil)) * 8;
-              bulk_load(sa + (size_t)pc * p.a_chunk_bytes + (size_t)j * row_bytes, src, row_bytes, &full[slot]);
-            }
-            if (lane == 0) {
-              const __half* wsrc = p.w + ((((size_t)cc * p.nk16 + k16) * p.kz + dz) * 3 + g * p.nky) * (size_t)(3 * 2 * 2 * NT * 8);
-              bulk_load(sa + 4 * (size_t)p.a_chunk_bytes, wsrc, p.w_bytes, &full[slot]);
-            }
           }
+          if (leader) umma_commit(&empty[slot]);  // frees the smem stage once every MMA above has read it
+          __syncwarp();
         }
       }
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ================================
-    if (lane == 0) {
-      const uint32_t idesc1 = make_idesc_f16(128, 2 * NT), idesc2 = make_idesc_f16(128, NT);
-      const uint32_t a_lbo = p.a_chunk_bytes, b_lbo = (uint32_t)(2 * NT * 16);
-      uint32_t it = 0, rs = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int d = (t / (p.ccs * p.tiles_x * p.tiles_y)) % p.D;
-        for (int k16 = 0; k16 < p.nk16; ++k16) {
-          for (int dz = 0; dz < p.kz; ++dz) {
-            const int zin = d + dz - zpad;
-            if (zin < 0 || zin >= p.D) continue;
-            for (int g = 0; g < kgroups; ++g, ++it) {
-              const int slot = it % p.nstages;
-              mbar_wait(&full[slot], (it / p.nstages) & 1);
-              tc_fence_after();
-              const uint32_t sa = smem_u32(smem + (size_t)slot * p.stage_bytes);
-              const uint64_t da_hi = make_smem_desc(sa, a_lbo, 128);
-              const uint64_t da_lo = make_smem_desc(sa + a_plane, a_lbo, 128);
-              const uint32_t sw = sa + 4 * p.a_chunk_bytes;
-#pragma unroll 1
-              for (int r = 0; r < R; ++r, ++rs) {
-                const uint32_t ts = rs % S;
-                mbar_wait(&row_empty[ts], ((rs / S) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t dcol = tmem_base + ts * (2 * NT);
-                uint32_t acc = 0;
-                for (int ky = 0; ky < p.nky; ++ky) {
-                  const int srow = p.nky == 1 ? r : (p.contig ? r + ky * p.dil : ky * R + r);
-                  for (int kx = 0; kx < 3; ++kx) {
-                    const uint64_t db = make_smem_desc(sw + (uint32_t)((ky * 3 + kx) * (2 * 2 * NT * 16)), b_lbo, 128);
-                    const uint32_t poff = (uint32_t)(srow * p.BW + kx * p.dil);      // 16-byte units
-                    umma_f16(dcol, da_hi + poff, db, idesc1, acc);
-                    umma_f16(dcol + NT, da_lo + poff, db, idesc2, 1u);
-                    acc = 1u;
-                  }
-                }
-                umma_commit(&row_full[ts]);      // this row's chain is complete once these MMAs retire
-              }
-              umma_commit(&empty[slot]);         // frees the smem slot once every MMA above has read it
-            }
-          }
-        }
-      }
-    }
+    if (p.prof && lane == 0) { p.prof[blockIdx.x * 16 + 4] = clock64() - t_start; p.prof[blockIdx.x * 16 + 5] = w_full; p.prof[blockIdx.x * 16 + 6] = w_slot; p.prof[blockIdx.x * 16 + 7] = rs; }
   } else if (warp >= 4) {
     // ================================ epilogue ================================
     const int wq = warp & 3;                  // TMEM lane quadrant this warp may read
-    const int hf = (warp - 4) >> 2;           // which half of the NT columns
+    const int hf = (warp - 4) >> 2;           // which 16 of the tile's 32 channels
     const int m = wq * 32 + lane;             // pixel within the 128-wide row segment
     const __half* res = static_cast<const __half*>(p.res.p);
     __half* out = static_cast<__half*>(p.out.p);
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + hf * 48;
     uint32_t rs = 0;
+    long long w_slotf = 0, t_fin = 0, t_start = clock64();
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      int q = t;
-      const int cc = q % p.ccs; q /= p.ccs;
-      const int tx = q % p.tiles_x; q /= p.tiles_x;
-      const int ty = q % p.tiles_y; q /= p.tiles_y;
-      const int d = q % p.D, n = q / p.D;
-      const int x = tx * 128 + m;
-      float acc[R][CW];
+      const TileCoord tc = decode_tile(p, t, R);
+      const int x = tc.tx * 128 + m;
+      float acc[R][16];
 #pragma unroll
       for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int c = 0; c < CW; ++c) acc[r][c] = 0.f;
+        for (int c = 0; c < 16; ++c) acc[r][c] = 0.f;
 
       for (int k16 = 0; k16 < p.nk16; ++k16) {
         for (int dz = 0; dz < p.kz; ++dz) {
-          const int zin = d + dz - zpad;
+          const int zin = tc.d + dz - zpad;
           if (zin < 0 || zin >= p.D) continue;
-          for (int g = 0; g < kgroups; ++g) {
 #pragma unroll
-            for (int r = 0; r < R; ++r, ++rs) {
-              const uint32_t ts = rs % S;
-              mbar_wait(&row_full[ts], (rs / S) & 1);
-              tc_fence_after();
-              const uint32_t col = lane_addr + ts * (2 * NT) + hf * CW;
+          for (int j = 0; j < BH; ++j, ++rs) {
+            const uint32_t ts = rs & 1;
+            { const long long c0 = clock64(); mbar_wait(&slot_full[ts], (rs >> 1) & 1); w_slotf += clock64() - c0; }
+            tc_fence_after();
+            const uint32_t col = lane_addr + ts * TC_SLOT_COLS;
 #pragma unroll
-              for (int c16 = 0; c16 < CW / 16; ++c16) {
-                float vm[16], vc[16];
-                tmem_ld_2x16(col + c16 * 16, col + NT + c16 * 16, vm, vc);
+            for (int ky = 0; ky < 3; ++ky) {
+              const int r = j - ky;             // input row j is kernel row ky of output row j - ky
+              if (r < 0 || r >= R) continue;
+              float vm[16], vc[16];
+              tmem_ld_2x16(col + ky * 16, col + TC_SLOT_COLS / 2 + ky * 16, vm, vc);
 #pragma unroll
-                for (int c = 0; c < 16; ++c) acc[r][c16 * 16 + c] += vm[c] + vc[c];
-              }
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&row_empty[ts]);
+              for (int c = 0; c < 16; ++c) acc[r][c] += vm[c] + vc[c];
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&slot_empty[ts]);
           }
         }
       }
 
       // bias (+ residual) (+ ReLU), split into hi/lo, 16-byte stores (a warp writes 512 contiguous bytes)
-      const int co0 = cc * NT + hf * CW;
+      const long long cfin = clock64();
+      const int co0 = tc.cc * NT + hf * 16;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const int y = ty * R + r;
-        if (y < p.H && x < p.W) {
+        const int y = tc.ybase + r * p.dil;
+        if (y < p.H && x < p.W && !(p.dbg & 4)) {
 #pragma unroll
-          for (int jb = 0; jb < CW / 8; ++jb) {
+          for (int jb = 0; jb < 2; ++jb) {
             const int cbo = (co0 >> 3) + jb;
-            const size_t pix = ((size_t)y * p.out.ws + x) * 8;
-            const size_t o = (size_t)n * p.out.ss + ((size_t)cbo * p.D + d) * p.out.slice + pix;
+            const size_t o = (size_t)tc.n * p.out.ss + ((size_t)cbo * p.D + tc.d) * p.out.slice + ((size_t)y * p.out.ws + x) * 8;
             float f[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = acc[r][jb * 8 + j] + __ldg(p.bias + co0 + jb * 8 + j);
             if (res) {
-              const size_t ro = (size_t)n * p.res.ss + ((size_t)cbo * p.D + d) * p.res.slice + ((size_t)y * p.res.ws + x) * 8;
+              const size_t ro = (size_t)tc.n * p.res.ss + ((size_t)cbo * p.D + tc.d) * p.res.slice + ((size_t)y * p.res.ws + x) * 8;
               const uint4 rh = __ldg(reinterpret_cast<const uint4*>(res + ro));
               const uint4 rl = __ldg(reinterpret_cast<const uint4*>(res + ro + p.res.lo));
               const __half2* h2 = reinterpret_cast<const __half2*>(&rh);
@@ -246,7 +270,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcConvParams p)
           }
         }
       }
+      t_fin += clock64() - cfin;
     }
+    if (p.prof && warp == 4 && lane == 0) { p.prof[blockIdx.x * 16 + 8] = clock64() - t_start; p.prof[blockIdx.x * 16 + 9] = w_slotf; p.prof[blockIdx.x * 16 + 10] = t_fin; }
   }
 
   tc_fence_before();
@@ -257,43 +283,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcConvParams p)
 // ---- host side -----------------------------------------------------------------------------------
 static const int SMEM_BUDGET = 227 * 1024 - 1024;
 
-// Fills BW/BH/stage sizes for (NT, R, nky); returns the number of pipeline stages that fit.
-static int tc_layout(TcConvParams& p, int NT, int R, int nky) {
-  p.NT = NT; p.R = R; p.nky = nky;
-  p.contig = (nky == 3 && p.dil < R) ? 1 : 0;
+static int tc_layout(TcConvParams& p, int R) {
+  p.R = R;
   p.BW = 128 + 2 * p.dil;
-  p.BH = nky == 1 ? R : (p.contig ? R + 2 * p.dil : 3 * R);
+  p.BH = R + 2;
   p.a_chunk_bytes = (uint32_t)(p.BH * p.BW * 16);
-  p.w_bytes = (uint32_t)(nky * 3 * 2 * 2 * NT * 16);
-  p.tx_bytes = 4 * p.a_chunk_bytes + p.w_bytes;
-  p.stage_bytes = (p.tx_bytes + 127) / 128 * 128;
-  const int S = 512 / (2 * NT);
-  const int fixed = 128 + (2 * 8 + 2 * S) * 8 + 16;
+  p.w_bytes = TC_W_BYTES;
+  p.stage_bytes = (4 * p.a_chunk_bytes + p.w_bytes + 127) / 128 * 128;
+  const int fixed = 128 + (2 * 8 + 4) * 8 + 16;
   int ns = (SMEM_BUDGET - fixed) / (int)p.stage_bytes;
-  return ns > 8 ? 8 : ns;
+  return ns > 4 ? 4 : ns;
 }
 
-// Chooses tile shape / pipeline depth for one convolution.  in: split-fp16 tensor with pad >= dil.
+// Chooses the tile height / pipeline depth for one convolution.  in: split-fp16 tensor with pad >= dil.
 cudaError_t tc_conv_plan(TcConvPlan* plan, const Tens& in, const Tens& out, int cin, int cout, int dil, int kz, int num_sms) {
-  if (cin % 16 || cout % 32 || in.planes != 2 || out.planes != 2 || in.pad < dil) return cudaErrorInvalidValue;
+  if (cin % 16 || cout % TC_NT || in.planes != 2 || out.planes != 2 || in.pad < dil) return cudaErrorInvalidValue;
   *plan = TcConvPlan();
   TcConvParams& p = plan->p;
   p.in = view(in); p.out = view(out);
   p.D = in.d; p.H = in.h; p.W = in.w; p.CBin = cin / 8; p.CBout = cout / 8; p.dil = dil; p.kz = kz; p.nk16 = cin / 16;
-  // one (NT, R) instantiation for now: 32 output channels x 4 rows per tile
-  const int NT = 32, R = 4;
-  int ns = tc_layout(p, NT, R, 3);
-  if (ns < 2) ns = tc_layout(p, NT, R, 1);
+  p.in_pad = in.pad;
+  p.ccs = cout / TC_NT;
+  p.tiles_x = cdiv(p.W, 128);
+  // 6 output rows per tile (8 input rows, 1.33x halo) when that still fills the GPU, else 2 rows for parallelism
+  auto tiles_for = [&](int R) { return (long)in.n * p.D * cdiv(p.H, R * dil) * dil * p.tiles_x * p.ccs; };
+  const int R = tiles_for(6) >= num_sms ? 6 : 2;
+  const int ns = tc_layout(p, R);
   if (ns < 1) return cudaErrorInvalidValue;
   p.nstages = ns;
-  if (R - 1 + 2 > TAIL_ROWS) return cudaErrorInvalidValue;
-  p.ccs = cout / NT;
-  p.tiles_x = cdiv(p.W, 128);
-  p.tiles_y = cdiv(p.H, R);
-  const int S = 512 / (2 * NT);
-  plan->smem = 128 + (size_t)p.nstages * p.stage_bytes + (size_t)(2 * p.nstages + 2 * S) * 8 + 16;
-  (void)num_sms;
+  p.tiles_y = cdiv(p.H, R * dil) * dil;
+  plan->smem = 128 + (size_t)p.nstages * p.stage_bytes + (size_t)(2 * p.nstages + 4) * 8 + 16;
   return cudaSuccess;
+}
+
+template <int R>
+static void launch_r(const TcConvParams& p, int grid, size_t smem, cudaStream_t st) {
+  static bool attr_done[32] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 31]) {
+    cudaFuncSetAttribute(k_conv_tc<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_done[dev & 31] = true;
+  }
+  k_conv_tc<R><<<grid, TC_THREADS, smem, st>>>(p);
 }
 
 cudaError_t launch_conv_tc(const TcConvPlan& plan, int N, const void* w, const float* bias, const Tens* res, int relu,
@@ -302,17 +334,36 @@ cudaError_t launch_conv_tc(const TcConvPlan& plan, int N, const void* w, const f
   p.N = N; p.w = static_cast<const __half*>(w); p.bias = bias; p.relu = relu;
   if (res) p.res = view(*res);
   p.total_tiles = N * p.D * p.tiles_y * p.tiles_x * p.ccs;
-  if (need_attr(8)) cudaFuncSetAttribute(k_conv_tc<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  { static const int dbg = getenv("SNB_TC_DEBUG") ? atoi(getenv("SNB_TC_DEBUG")) : 0; p.dbg = dbg; }
+  static const int prof = getenv("SNB_TC_PROF") ? atoi(getenv("SNB_TC_PROF")) : 0;
+  static long long* d_prof = nullptr;
+  if (prof && !d_prof) cudaMalloc(&d_prof, 256 * 16 * sizeof(long long));
+  p.prof = prof ? d_prof : nullptr;
+  if (prof) cudaMemsetAsync(d_prof, 0, 256 * 16 * sizeof(long long), st);
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  k_conv_tc<32, 4><<<grid, TC_THREADS, plan.smem, st>>>(p);
+  if (p.R == 6) launch_r<6>(p, grid, plan.smem, st);
+  else launch_r<2>(p, grid, plan.smem, st);
+  if (prof) {     // diagnostics only: synchronous read-back, max over CTAs of each role's counters
+    cudaStreamSynchronize(st);
+    std::vector<long long> h(grid * 16);
+    cudaMemcpy(h.data(), d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    long long mx[16] = {0};
+    for (int b = 0; b < grid; ++b) for (int k = 0; k < 16; ++k) mx[k] = std::max(mx[k], h[b * 16 + k]);
+    fprintf(stderr, "[tcprof] H%d W%d D%d Cin%d Cout%d dil%d res%d R%d tiles %d grid %d | producer total %lld wait_empty %lld stages %lld | "
+            "issuer total %lld wait_full %lld wait_slot_empty %lld rows %lld | epilogue total %lld wait_slot_full %lld finalize %lld\n",
+            p.H, p.W, p.D, p.CBin * 8, p.CBout * 8, p.dil, res ? 1 : 0, p.R, p.total_tiles, grid, mx[0], mx[1], mx[2], mx[4], mx[5], mx[6], mx[7],
+            mx[8], mx[9], mx[10]);
+  }
   return cudaGetLastError();
 }
 
-// Weight packing for k_conv_tc: [cc][k16][dz][ky][kx][chunk 2][W_hi NT rows | W_lo NT rows][8] fp16,
-// from canonical [Cout][Cin][kz][3][3] fp32.
+// Weight packing for k_conv_tc: [cc][k16][dz][kx][chunk 2][192 rows][8] fp16 from canonical
+// [Cout][Cin][kz][3][3] fp32; row = part*96 + half*48 + ky*16 + (co % 16), part 0 = W_hi, 1 = W_lo,
+// half = which 16 of the tile's 32 channels (one epilogue warp set each).
 void tc_pack_weights(const float* W, int cout, int cin, int kz, int NT, std::vector<__half>& out) {
-  const int ccs = cout / NT, nk16 = cin / 16;
-  out.assign((size_t)ccs * nk16 * kz * 3 * 3 * 2 * 2 * NT * 8, __float2half(0.f));
+  (void)NT;
+  const int ccs = cout / TC_NT, nk16 = cin / 16;
+  out.assign((size_t)ccs * nk16 * kz * 3 * 2 * TC_SLOT_COLS * 8, __float2half(0.f));
   for (int co = 0; co < cout; ++co)
     for (int ci = 0; ci < cin; ++ci)
       for (int dz = 0; dz < kz; ++dz)
@@ -321,11 +372,11 @@ void tc_pack_weights(const float* W, int cout, int cin, int kz, int NT, std::vec
             const float v = W[((((size_t)co * cin + ci) * kz + dz) * 3 + ky) * 3 + kx];
             const __half hi = __float2half_rn(v);
             const __half lo = __float2half_rn(v - __half2float(hi));
-            const int cc = co / NT, nn = co % NT, k16 = ci / 16, chunk = (ci % 16) / 8, e = ci % 8;
-            const size_t tap = (((((size_t)cc * nk16 + k16) * kz + dz) * 3 + ky) * 3 + kx);
-            const size_t base = (tap * 2 + chunk) * (size_t)(2 * NT);
-            out[(base + nn) * 8 + e] = hi;
-            out[(base + NT + nn) * 8 + e] = lo;
+            const int cc = co / TC_NT, cl = co % TC_NT, k16 = ci / 16, chunk = (ci % 16) / 8, e = ci % 8;
+            const int row = (cl / 16) * 48 + ky * 16 + cl % 16;
+            const size_t blk = ((((size_t)cc * nk16 + k16) * kz + dz) * 3 + kx) * 2 + chunk;
+            out[(blk * TC_SLOT_COLS + row) * 8 + e] = hi;
+            out[(blk * TC_SLOT_COLS + 96 + row) * 8 + e] = lo;
           }
 }
 

@@ -184,7 +184,7 @@ struct Builder {
       TcConvPlan plan;
       cudaError_t e = tc_conv_plan(&plan, in, out, cw.cin, cw.cout, dil, cw.kz, c->num_sms);
       if (e != cudaSuccess) { fail = true; snprintf(c->err, sizeof(c->err), "tc_conv_plan(%s): %s", name.c_str(), cudaGetErrorString(e)); return out; }
-      const int NT = plan.p.NT;
+      const int NT = 32;   // k_conv_tc tile width (one packing)
       if (!cw.w_tc.count(NT)) {
         std::vector<__half> packed;
         tc_pack_weights(c->wts[name + ".weight"].data.data(), cw.cout, cw.cin, cw.kz, NT, packed);

@@ -9,6 +9,11 @@
 
 using namespace snb::ptx;
 
+__device__ __forceinline__ void umma_acc(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc) : "memory");
+}
+
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {   // K-major, 128B swizzle, SBO = 1024
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3fff);
@@ -37,7 +42,9 @@ __global__ void __launch_bounds__(128, 1) k_bench(int shift16, int iters, int mo
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = slot;
-  if (threadIdx.x == 0) {
+  if (warp == 1) {
+   const bool leader = elect_one();
+   if (leader) {
     const uint32_t sa = smem_u32(smem), sb = sa + 96 * 1024;
     const uint32_t idesc = make_idesc_f16(128, N);
     uint64_t da0, db0;
@@ -50,11 +57,11 @@ __global__ void __launch_bounds__(128, 1) k_bench(int shift16, int iters, int mo
     const long long t0 = clock64();
     for (int i = 0; i < iters; i += 3 * NACC) {
 #pragma unroll
-      for (int a = 0; a < NACC; ++a) umma_f16(tm + a * N, da0, db0, idesc, 1u);
+      for (int a = 0; a < NACC; ++a) umma_acc(tm + a * N, da0, db0, idesc);
 #pragma unroll
-      for (int a = 0; a < NACC; ++a) umma_f16(tm + a * N, da1, db0, idesc, 1u);
+      for (int a = 0; a < NACC; ++a) umma_acc(tm + a * N, da1, db0, idesc);
 #pragma unroll
-      for (int a = 0; a < NACC; ++a) umma_f16(tm + a * N, da2, db0, idesc, 1u);
+      for (int a = 0; a < NACC; ++a) umma_acc(tm + a * N, da2, db0, idesc);
     }
     const long long t1 = clock64();
     umma_commit(&bar);
@@ -62,6 +69,7 @@ __global__ void __launch_bounds__(128, 1) k_bench(int shift16, int iters, int mo
     const long long t2 = clock64();
     out[blockIdx.x * 2] = t1 - t0;
     out[blockIdx.x * 2 + 1] = t2 - t0;
+   }
   }
   tc_fence_before();
   __syncthreads();
