@@ -143,7 +143,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("SNB_PRECISION", "fp32"), choices=["fp32", "tc"])
+    ap.add_argument("--precision", default=os.environ.get("SNB_PRECISION", "tc"), choices=["fp32", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -168,22 +168,12 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- init (untimed): rank 0 builds the weight blob, one NCCL broadcast installs it everywhere ----
-    blob_t = None
-    if rank == 0:
-        blob = capi.synthesize_weights(K, SEED)      # a deployment passes model_file instead
-        blob_t = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
-        nbytes = torch.tensor([blob_t.numel()], device=dev, dtype=torch.int64)
-    else:
-        nbytes = torch.zeros(1, device=dev, dtype=torch.int64)
-    if world > 1:
-        dist.broadcast(nbytes, 0)
-        if rank != 0:
-            blob_t = torch.empty(int(nbytes.item()), dtype=torch.uint8, device=dev)
-        dist.broadcast(blob_t, 0)                    # the single collective of this workload
+    from hobot_stereonet_b200.shard import broadcast_blob
+    blob = capi.synthesize_weights(K, SEED) if rank == 0 else None      # a deployment passes model_file instead
+    blob = broadcast_blob(blob, src=0, device=dev)                        # the single collective of this workload
     prec = capi.PREC_TC_F16X2 if args.precision == "tc" else capi.PREC_FP32
-    m = Model(H, W, K, D, max_batch=BATCH, device=local_rank, task_num=4, precision=prec,
-              weights=bytes(blob_t.cpu().numpy().tobytes()))
-    del blob_t
+    m = Model(H, W, K, D, max_batch=BATCH, device=local_rank, task_num=4, precision=prec, weights=blob)
+    del blob
 
     # ---- inputs: a rotating pool larger than L2, so no step finds its input cached ----
     in_bytes = 6 * H * W * BATCH
