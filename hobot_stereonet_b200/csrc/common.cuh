@@ -104,6 +104,20 @@ struct TcConvParams {    // k_conv_tc.cu
 };
 struct TcConvPlan { TcConvParams p; size_t smem; };
 
+struct RbParams {        // k_resblock_tc.cu: fused 32-channel residual block
+  TV in, out, res;       // split-fp16 tensors, 4 channel blocks, D = 1
+  const __half* wa; const __half* wb;     // tc_pack_weights layout of conv_a / conv_b
+  const float* ba; const float* bb;
+  int N, H, W, dil, in_pad;
+  int OW, XW;            // output pixels per strip (128 - 2 dil), staged pixels per row (128 + 2 dil)
+  int strips, nchunk, rpc, total_units;   // units = (sample, strip, comb, row chunk of rpc comb rows)
+  int nxs;               // depth of the x-row ring
+  uint32_t sub_bytes, slot_bytes;         // one (plane, chunk) row, one ring slot (8 of them)
+  long long* prof;       // SNB_TC_PROF=1: per-CTA cycle counters of the issuer and epilogue roles
+  int dbg;               // timing experiments only (env SNB_RB_DEBUG): 1 no proxy fence, 2 no y stores, 4 no global stores, 8 no residual loads
+};
+struct RbPlan { RbParams p; size_t smem; int num_sms; };
+
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 // true the first time kernel slot `k` is launched on the current device (opt-in smem attribute)

@@ -1,0 +1,448 @@
+// Fused residual block on the tcgen05 tensor cores (SNB_PREC_TC_F16X2), 32 channels:
+//     out = ReLU( conv_b( ReLU( conv_a(x) + ba ) ) + bb + res )          conv_a, conv_b: 3x3, dilation d
+// i.e. one edge-aware-refinement "residual_astrous_block" (hbm `_head_edge_aware_refinements_*_residual_astrous_blocks_*`)
+// or one 32-channel backbone BasicBlock (`_backbone_layer1_*`), SURVEY.md §8a rows M5 / M1, in ONE pass over x:
+// the intermediate activation never goes to HBM, and the block moves 8 B/element instead of 20.
+//
+//   streaming     a CTA owns a strip of 128-2d output columns and walks DOWN the rows of one comb (rows d apart,
+//                 so vertical taps stay inside the comb).  Per row it runs two "jobs" on the tensor core:
+//                   a-job(i): x row i  (smem ring, bulk-copied)  x  Wa  -> contribution to y rows i-1, i, i+1
+//                   b-job(i): y row i  (smem ring, written by epilogue group A) x Wb -> out rows i-1, i, i+1
+//                 GEMM view: M = 128 pixels of the input row, N = 32 channels x 3 kernel rows = 96, K = 16
+//                 channels per MMA; the kernel column is a 16-byte shift of the A descriptor.  A job is 18 MMAs
+//                 (2 channel chunks x 3 columns x {hi*hi, hi*lo, lo*hi}) chained in ONE 96-column TMEM slot.
+//   halo          only 4 extra rows at the top of a column walk (two per conv) instead of 2 per 6-row tile twice.
+//   epilogue      two warp groups, one per conv, so the y emission and the output emission overlap:
+//                 group A (warps 2-5) drains a-jobs, keeps two partial y rows in fp32 registers; a finished row gets
+//                 ReLU, zero outside the image (conv_b's zero padding), hi/lo fp16 split, and goes into the y ring
+//                 in the A-operand layout.  Group B (warps 6-9) drains b-jobs; a finished output row gets the
+//                 residual, ReLU, the split, and goes to HBM.  Biases are added when a partial row is born.
+//   pipeline      warp 0: bulk-copy producer (weights once, then one x row per a-job), warp 1: TMEM owner + MMA
+//                 issuer.  TMEM: 3 slots for a-jobs + 2 for b-jobs (5 x 96 columns), full/empty mbarriers each.
+//                 Persistent over (sample, strip, comb, row-chunk) units.
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "tc_ptx.cuh"
+
+namespace snb {
+
+using namespace ptx;
+
+constexpr int RB_THREADS = 320;
+constexpr int RB_GROUP_WARPS = 4;
+constexpr int RB_SLOT_COLS = 96;                        // [half][ky][16 ch]
+constexpr int RB_WROWS = 192;                           // packed weight rows per (k16, kx, chunk): [W_hi 96 | W_lo 96]
+constexpr uint32_t RB_W_BYTES = 2 * 3 * 2 * RB_WROWS * 16;   // one conv: [k16][kx][chunk][192 rows][8 halfs]
+constexpr int RB_YSLOTS = 3, RB_ASLOTS = 3, RB_BSLOTS = 2;
+
+struct RbUnit { int n, x0, c, i0, nr; };
+
+__device__ __forceinline__ RbUnit rb_decode(const RbParams& p, int u) {
+  RbUnit r;
+  const int chunk = u % p.nchunk; u /= p.nchunk;
+  r.c = u % p.dil; u /= p.dil;
+  const int strip = u % p.strips;
+  r.n = u / p.strips;
+  r.x0 = strip * p.OW;
+  const int rc = r.c < p.H ? (p.H - r.c + p.dil - 1) / p.dil : 0;     // rows of this comb
+  r.i0 = chunk * p.rpc;
+  const int i1 = min(rc, r.i0 + p.rpc);
+  r.nr = i1 - r.i0;
+  return r;
+}
+
+// Three 32-lane x 16-column fp32 loads (kernel rows 0..2 of one 16-channel half) and the wait in one asm statement.
+__device__ __forceinline__ void rb_drain(uint32_t col, float (&v0)[16], float (&v1)[16], float (&v2)[16]) {
+  uint32_t r[48];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%48];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%49];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47}, [%50];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
+        "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+        "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47])
+      : "r"(col), "r"(col + 16), "r"(col + 32) : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { v0[i] = __uint_as_float(r[i]); v1[i] = __uint_as_float(r[16 + i]); v2[i] = __uint_as_float(r[32 + i]); }
+}
+
+__device__ __forceinline__ void rb_split8(const float* f, uint4& oh, uint4& ol) {
+  __half2* ph = reinterpret_cast<__half2*>(&oh);
+  __half2* pl = reinterpret_cast<__half2*>(&ol);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __half2 hh = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+    const float2 hf = __half22float2(hh);
+    ph[j] = hh;
+    pl[j] = __floats2half2_rn(f[2 * j] - hf.x, f[2 * j + 1] - hf.y);
+  }
+}
+
+__device__ __forceinline__ void rb_sts16(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <bool PROF>
+__global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ float s_bias[64];                 // [ba 32 | bb 32]
+  __shared__ uint64_t bars[40];
+  __shared__ uint32_t tmem_slot;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  uint8_t* s_wa = smem;
+  uint8_t* s_wb = smem + RB_W_BYTES;
+  uint8_t* s_x = smem + 2 * RB_W_BYTES;
+  uint8_t* s_y = s_x + (size_t)p.nxs * p.slot_bytes;
+  uint64_t* w_full = bars;
+  uint64_t* x_full = bars + 1;
+  uint64_t* x_empty = x_full + p.nxs;          // nxs <= 8
+  uint64_t* y_full = bars + 17;
+  uint64_t* y_empty = y_full + RB_YSLOTS;
+  uint64_t* sa_full = y_empty + RB_YSLOTS;
+  uint64_t* sa_empty = sa_full + RB_ASLOTS;
+  uint64_t* sb_full = sa_empty + RB_ASLOTS;
+  uint64_t* sb_empty = sb_full + RB_BSLOTS;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    mbar_init(w_full, 1);
+    for (int i = 0; i < p.nxs; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+    for (int i = 0; i < RB_YSLOTS; ++i) { mbar_init(&y_full[i], RB_GROUP_WARPS); mbar_init(&y_empty[i], 1); }
+    for (int i = 0; i < RB_ASLOTS; ++i) { mbar_init(&sa_full[i], 1); mbar_init(&sa_empty[i], RB_GROUP_WARPS); }
+    for (int i = 0; i < RB_BSLOTS; ++i) { mbar_init(&sb_full[i], 1); mbar_init(&sb_empty[i], RB_GROUP_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
+  if (threadIdx.x >= 64 && threadIdx.x < 128) s_bias[threadIdx.x - 64] = threadIdx.x < 96 ? p.ba[threadIdx.x - 64] : p.bb[threadIdx.x - 96];
+  // the y ring's columns >= 128 are read by shifted taps of masked pixels only; keep them finite
+  for (int i = threadIdx.x; i < (int)(RB_YSLOTS * p.slot_bytes / 16); i += RB_THREADS)
+    reinterpret_cast<uint4*>(s_y)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const int d = p.dil;
+  long long t_start = 0, tw0 = 0, tw1 = 0, tw2 = 0, tw3 = 0;
+  if (PROF) t_start = clock64();
+#define RB_WAIT(acc, bar, par) do { if (PROF) { const long long _c = clock64(); mbar_wait(bar, par); acc += clock64() - _c; } else mbar_wait(bar, par); } while (0)
+
+  if (warp == 0) {
+    // ================================ bulk-copy producer ================================
+    if (lane == 0) {
+      mbar_expect_tx(w_full, 2 * RB_W_BYTES);
+      bulk_load(s_wa, p.wa, RB_W_BYTES, w_full);
+      bulk_load(s_wb, p.wb, RB_W_BYTES, w_full);
+    }
+    const __half* in = static_cast<const __half*>(p.in.p);
+    uint32_t itx = 0;
+    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+      const RbUnit un = rb_decode(p, u);
+      if (un.nr <= 0) continue;
+      const __half* src0 = in + (size_t)un.n * p.in.ss + (size_t)((lane >> 2) & 1) * p.in.lo + (size_t)(lane & 3) * p.in.slice +
+                           (ptrdiff_t)(un.x0 - 2 * d) * 8;
+      for (int ja = 0; ja < un.nr + 4; ++ja, ++itx) {
+        int row = un.c + d * (un.i0 - 2 + ja);
+        row = min(row, p.H + p.in_pad - 1);       // rows past the bottom border only feed y rows that are forced to zero
+        const uint32_t slot = itx % p.nxs;
+        if (lane == 0) {
+          mbar_wait(&x_empty[slot], ((itx / p.nxs) & 1) ^ 1);
+          mbar_expect_tx(&x_full[slot], 8 * p.sub_bytes);
+        }
+        __syncwarp();
+        if (lane < 8)
+          bulk_load(s_x + (size_t)slot * p.slot_bytes + (size_t)lane * p.sub_bytes, src0 + (ptrdiff_t)row * p.in.ws * 8, p.sub_bytes,
+                    &x_full[slot]);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_f16(128, RB_SLOT_COLS);
+    const uint32_t b_lbo = RB_WROWS * 16;
+    const uint32_t dil16 = (uint32_t)d;                     // descriptor address units of 16 B = one pixel
+    const uint32_t wa_addr = smem_u32(s_wa), wb_addr = smem_u32(s_wb);
+    mbar_wait(w_full, 0);
+    uint32_t na = 0, nb = 0, itx = 0;
+
+    // 18 MMAs of one job: A rows from `a_addr` ([plane][chunk][px][8]), weights from `w_addr`, one accumulator
+    auto issue_job = [&](uint32_t a_addr, uint32_t w_addr, uint32_t dcol) {
+#pragma unroll
+      for (int k16 = 0; k16 < 2; ++k16) {
+        const uint64_t a_hi = make_smem_desc(a_addr + (uint32_t)(2 * k16) * p.sub_bytes, p.sub_bytes, 128);
+        const uint64_t a_lo = make_smem_desc(a_addr + (uint32_t)(4 + 2 * k16) * p.sub_bytes, p.sub_bytes, 128);
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const uint64_t w_hi = make_smem_desc(w_addr + (uint32_t)((k16 * 3 + kx) * 2) * b_lbo, b_lbo, 128);
+          const uint64_t w_lo = w_hi + (uint64_t)RB_SLOT_COLS;        // +96 rows x 16 B, in 16-byte units
+          const uint64_t sh = (uint64_t)(kx * dil16);
+          if (k16 == 0 && kx == 0) umma_f16_zero(dcol, a_hi, w_hi, idesc);
+          else umma_f16_acc(dcol, a_hi + sh, w_hi, idesc);
+          umma_f16_acc(dcol, a_hi + sh, w_lo, idesc);
+          umma_f16_acc(dcol, a_lo + sh, w_hi, idesc);
+        }
+      }
+    };
+
+    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+      const RbUnit un = rb_decode(p, u);
+      if (un.nr <= 0) continue;
+      for (int step = 0; step < un.nr + 5; ++step) {
+        if (step < un.nr + 4) {                            // a-job: x row i0 - 2 + step
+          const uint32_t slot = itx % p.nxs, ts = na % RB_ASLOTS;
+          RB_WAIT(tw0, &x_full[slot], (itx / p.nxs) & 1);
+          RB_WAIT(tw1, &sa_empty[ts], ((na / RB_ASLOTS) & 1) ^ 1);
+          tc_fence_after();
+          if (leader) {
+            issue_job(smem_u32(s_x + (size_t)slot * p.slot_bytes), wa_addr, tmem_base + ts * RB_SLOT_COLS);
+            umma_commit(&sa_full[ts]);
+            umma_commit(&x_empty[slot]);
+          }
+          __syncwarp();
+          ++itx; ++na;
+        }
+        if (step >= 3 && step - 3 < un.nr + 2) {           // b-job: y row i0 - 1 + (step - 3)
+          const uint32_t ys = nb % RB_YSLOTS, ts = nb % RB_BSLOTS;
+          RB_WAIT(tw2, &y_full[ys], (nb / RB_YSLOTS) & 1);
+          RB_WAIT(tw3, &sb_empty[ts], ((nb / RB_BSLOTS) & 1) ^ 1);
+          tc_fence_after();
+          if (leader) {
+            issue_job(smem_u32(s_y + (size_t)ys * p.slot_bytes), wb_addr, tmem_base + (RB_ASLOTS + ts) * RB_SLOT_COLS);
+            umma_commit(&sb_full[ts]);
+            umma_commit(&y_empty[ys]);
+          }
+          __syncwarp();
+          ++nb;
+        }
+      }
+    }
+    if (PROF && lane == 0) {
+      long long* q = p.prof + blockIdx.x * 24;
+      q[0] = clock64() - t_start; q[1] = tw0; q[2] = tw1; q[3] = tw2; q[4] = tw3; q[5] = na + nb;
+    }
+  } else if (warp < 2 + RB_GROUP_WARPS) {
+    // ================================ epilogue group A: a-jobs -> y rows ================================
+    const int m = (warp & 3) * 32 + lane;     // TMEM lane = M row = pixel within the 128-wide window
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t sy_addr = smem_u32(s_y) + (uint32_t)m * 16;
+    uint32_t na = 0, ny = 0;
+    long long t_emit = 0;
+    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+      const RbUnit un = rb_decode(p, u);
+      if (un.nr <= 0) continue;
+      float a0[32], a1[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) a0[c] = a1[c] = 0.f;
+      const int ypx = un.x0 - d + m;          // image column of this thread's y pixel
+      const bool col_ok = ypx >= 0 && ypx < p.W;
+      for (int ja = 0; ja < un.nr + 4; ++ja, ++na) {
+        const uint32_t ts = na % RB_ASLOTS, ys = ny % RB_YSLOTS;             // y rows are emitted from ja = 2 on
+        const int row = un.c + d * (un.i0 - 3 + ja);
+        const bool ok = col_ok && row >= 0 && row < p.H;
+        RB_WAIT(tw0, &sa_full[ts], (na / RB_ASLOTS) & 1);
+        tc_fence_after();
+        if (ja >= 2) RB_WAIT(tw1, &y_empty[ys], ((ny / RB_YSLOTS) & 1) ^ 1);
+        const long long c0 = PROF ? clock64() : 0;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          float v0[16], v1[16], v2[16];
+          rb_drain(lane_addr + ts * RB_SLOT_COLS + hf * 48, v0, v1, v2);
+          if (hf == 1) {                       // the slot is in registers: hand it back to the issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sa_empty[ts]);
+          }
+          if (ja >= 2) {
+#pragma unroll
+            for (int jb = 0; jb < 2; ++jb) {
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = ok ? fmaxf(a0[hf * 16 + jb * 8 + j] + v2[jb * 8 + j], 0.f) : 0.f;
+              uint4 oh, ol;
+              rb_split8(f, oh, ol);
+              const uint32_t a = sy_addr + ys * p.slot_bytes + (uint32_t)(hf * 2 + jb) * p.sub_bytes;
+              rb_sts16(a, oh);
+              rb_sts16(a + 4 * p.sub_bytes, ol);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) { a0[hf * 16 + c] = a1[hf * 16 + c] + v1[c]; a1[hf * 16 + c] = v0[c] + s_bias[hf * 16 + c]; }
+        }
+        if (ja >= 2) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&y_full[ys]);
+          ++ny;
+        }
+        if (PROF) t_emit += clock64() - c0;
+      }
+    }
+    if (PROF && warp == 2 && lane == 0) {
+      long long* q = p.prof + blockIdx.x * 24;
+      q[8] = clock64() - t_start; q[9] = tw0; q[10] = tw1; q[11] = t_emit;
+    }
+  } else {
+    // ================================ epilogue group B: b-jobs -> output rows ================================
+    const int m = (warp & 3) * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + RB_ASLOTS * RB_SLOT_COLS;
+    const __half* res = static_cast<const __half*>(p.res.p);
+    __half* out = static_cast<__half*>(p.out.p);
+    uint32_t nb = 0;
+    long long t_emit = 0;
+    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+      const RbUnit un = rb_decode(p, u);
+      if (un.nr <= 0) continue;
+      float b0[32], b1[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) b0[c] = b1[c] = 0.f;
+      const int opx = un.x0 + m;              // image column of this thread's output pixel
+      const bool col_ok = m < p.OW && opx < p.W;
+      const size_t r_base = (size_t)un.n * p.res.ss + (size_t)opx * 8;
+      const size_t o_base = (size_t)un.n * p.out.ss + (size_t)opx * 8;
+      for (int jb_ = 0; jb_ < un.nr + 2; ++jb_, ++nb) {
+        const uint32_t ts = nb % RB_BSLOTS;
+        const int io = jb_ - 2;
+        const int row = un.c + d * (un.i0 + io);
+        const bool ok = col_ok && io >= 0 && row < p.H;
+        uint4 rh[4], rl[4];
+        if (ok) {                                          // residual prefetch: in flight while the job's MMAs finish
+          const __half* rp = res + r_base + (size_t)row * p.res.ws * 8;
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb) {
+            rh[cb] = __ldg(reinterpret_cast<const uint4*>(rp + (size_t)cb * p.res.slice));
+            rl[cb] = __ldg(reinterpret_cast<const uint4*>(rp + (size_t)cb * p.res.slice + p.res.lo));
+          }
+        }
+        RB_WAIT(tw0, &sb_full[ts], (nb / RB_BSLOTS) & 1);
+        tc_fence_after();
+        const long long c0 = PROF ? clock64() : 0;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          float v0[16], v1[16], v2[16];
+          rb_drain(lane_addr + ts * RB_SLOT_COLS + hf * 48, v0, v1, v2);
+          if (hf == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sb_empty[ts]);
+          }
+          if (ok) {
+            __half* op = out + o_base + (size_t)row * p.out.ws * 8;
+#pragma unroll
+            for (int jb = 0; jb < 2; ++jb) {
+              const int cb = hf * 2 + jb;
+              const __half2* h2 = reinterpret_cast<const __half2*>(&rh[cb]);
+              const __half2* l2 = reinterpret_cast<const __half2*>(&rl[cb]);
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 a = __half22float2(h2[j]), b = __half22float2(l2[j]);
+                const int c = jb * 8 + 2 * j;
+                f[2 * j] = fmaxf(b0[hf * 16 + c] + v2[c] + (a.x + b.x), 0.f);
+                f[2 * j + 1] = fmaxf(b0[hf * 16 + c + 1] + v2[c + 1] + (a.y + b.y), 0.f);
+              }
+              uint4 oh, ol;
+              rb_split8(f, oh, ol);
+              *reinterpret_cast<uint4*>(op + (size_t)cb * p.out.slice) = oh;
+              *reinterpret_cast<uint4*>(op + (size_t)cb * p.out.slice + p.out.lo) = ol;
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) { b0[hf * 16 + c] = b1[hf * 16 + c] + v1[c]; b1[hf * 16 + c] = v0[c] + s_bias[32 + hf * 16 + c]; }
+        }
+        if (PROF) t_emit += clock64() - c0;
+      }
+    }
+    if (PROF && warp == 6 && lane == 0) {
+      long long* q = p.prof + blockIdx.x * 24;
+      q[16] = clock64() - t_start; q[17] = tw0; q[18] = t_emit;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+// in/out/res: split-fp16 C8 tensors with 32 channels, d = 1, same H x W; in.pad >= 2*dil.
+cudaError_t resblock_tc_plan(RbPlan* plan, const Tens& in, const Tens& out, const Tens& res, int dil, int num_sms) {
+  if (in.planes != 2 || out.planes != 2 || res.planes != 2 || in.cb != 4 || out.cb != 4 || res.cb != 4 || in.d != 1 ||
+      in.pad < 2 * dil || dil < 1 || dil > 16 || out.h != in.h || out.w != in.w || res.h != in.h || res.w != in.w)
+    return cudaErrorInvalidValue;
+  *plan = RbPlan();
+  RbParams& p = plan->p;
+  p.in = view(in); p.out = view(out); p.res = view(res);
+  p.H = in.h; p.W = in.w; p.dil = dil; p.in_pad = in.pad;
+  p.OW = 128 - 2 * dil;
+  p.XW = 128 + 2 * dil;
+  p.sub_bytes = (uint32_t)p.XW * 16;
+  p.slot_bytes = 8 * p.sub_bytes;
+  p.strips = cdiv(p.W, p.OW);
+  plan->num_sms = num_sms;
+  const size_t fixed = 128 + 2 * (size_t)RB_W_BYTES + (size_t)RB_YSLOTS * p.slot_bytes;
+  int nxs = (int)((227 * 1024 - 2048 - fixed) / p.slot_bytes);       // 2 KB: static shared (biases, barriers) + slack
+  nxs = nxs > 6 ? 6 : nxs;
+  if (nxs < 3) return cudaErrorInvalidValue;
+  p.nxs = nxs;
+  plan->smem = fixed + (size_t)nxs * p.slot_bytes;
+  return cudaSuccess;
+}
+
+cudaError_t launch_resblock_tc(const RbPlan& plan, int N, const void* wa, const void* wb, const float* ba, const float* bb,
+                               cudaStream_t st) {
+  RbParams p = plan.p;
+  p.N = N; p.wa = static_cast<const __half*>(wa); p.wb = static_cast<const __half*>(wb); p.ba = ba; p.bb = bb;
+  // row chunks: about one unit per SM; every unit pays 4 halo rows, so never chop below 4 rows when avoidable
+  const int rc_max = cdiv(p.H, p.dil);
+  const int columns = N * p.strips * p.dil;                 // independent column walks
+  int nchunk = plan.num_sms / columns;                      // floor: never spill a few units into a second wave
+  if (nchunk < 1) nchunk = 1;
+  if (nchunk > cdiv(rc_max, 4)) nchunk = cdiv(rc_max, 4);
+  p.rpc = cdiv(rc_max, nchunk);
+  p.nchunk = cdiv(rc_max, p.rpc);
+  p.total_units = columns * p.nchunk;
+  static bool attr_done[32] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 31]) {
+    cudaFuncSetAttribute(k_resblock_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);   // static shared: 592 B
+    cudaFuncSetAttribute(k_resblock_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    attr_done[dev & 31] = true;
+  }
+  const int grid = p.total_units < plan.num_sms ? p.total_units : plan.num_sms;
+  static const int prof = getenv("SNB_TC_PROF") ? atoi(getenv("SNB_TC_PROF")) : 0;
+  if (!prof) {
+    k_resblock_tc<false><<<grid, RB_THREADS, plan.smem, st>>>(p);
+    return cudaGetLastError();
+  }
+  // diagnostics only: per-role cycle counters, synchronous read-back, max over CTAs
+  static long long* d_prof = nullptr;
+  if (!d_prof) cudaMalloc(&d_prof, 256 * 24 * sizeof(long long));
+  p.prof = d_prof;
+  cudaMemsetAsync(d_prof, 0, 256 * 24 * sizeof(long long), st);
+  k_resblock_tc<true><<<grid, RB_THREADS, plan.smem, st>>>(p);
+  cudaStreamSynchronize(st);
+  std::vector<long long> h(grid * 24);
+  cudaMemcpy(h.data(), d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+  long long mx[24] = {0};
+  for (int b = 0; b < grid; ++b) for (int k = 0; k < 24; ++k) mx[k] = std::max(mx[k], h[b * 24 + k]);
+  fprintf(stderr, "[rbprof] H%d W%d dil%d N%d units %d (rpc %d) grid %d | issuer total %lld wait_x %lld wait_slot(a) %lld wait_y %lld wait_slot(b) %lld jobs %lld | "
+          "groupA total %lld wait_full %lld wait_y_empty %lld drain+emit %lld | groupB total %lld wait_full %lld drain+emit %lld\n",
+          p.H, p.W, p.dil, N, p.total_units, p.rpc, grid, mx[0], mx[1], mx[2], mx[3], mx[4], mx[5], mx[8], mx[9], mx[10], mx[11],
+          mx[16], mx[17], mx[18]);
+  return cudaGetLastError();
+}
+
+}  // namespace snb

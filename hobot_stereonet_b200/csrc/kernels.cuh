@@ -14,6 +14,11 @@ cudaError_t launch_conv_tc(const TcConvPlan& plan, int N, const void* w, const f
                            int num_sms, cudaStream_t st);
 void tc_pack_weights(const float* W, int cout, int cin, int kz, int NT, std::vector<__half>& out);
 
+// k_resblock_tc.cu — fused residual block (conv_a + ReLU + conv_b + residual + ReLU), 32 channels (M1 layer1, M5)
+cudaError_t resblock_tc_plan(RbPlan* plan, const Tens& in, const Tens& out, const Tens& res, int dil, int num_sms);
+cudaError_t launch_resblock_tc(const RbPlan& plan, int N, const void* wa, const void* wb, const float* ba, const float* bb,
+                               cudaStream_t st);
+
 // k_mem.cu — HBM-bound kernels
 // P3 tail on device: s8 NCHW [B,6,H,W] -> C8 [2B][1][Hp][Wp][8] (x/128; left n<B, right n>=B; ch 3..7 = 0)
 cudaError_t launch_pre_s8(const int8_t* s8, Tens img, int B, int H, int W, cudaStream_t st);

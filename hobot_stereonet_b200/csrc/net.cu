@@ -15,7 +15,7 @@ static const int LAYER_BLOCKS[4] = {3, 16, 3, 3};
 static const int LAYER_CH[4] = {32, 64, 128, 128};
 static const int REF_DIL[6] = {1, 2, 4, 8, 1, 1};
 // zero border (pixels) of the padded C8 layout: >= the largest dilation of any tcgen05 consumer
-static const int PAD_BACKBONE = 2, PAD_REFINE = 8;
+static const int PAD_BACKBONE = 2, PAD_REFINE = 16;   // the fused residual block reads a 2*dilation halo
 
 // ---- weight blob ("SNB2WGT1", oracle/weights.py documents the layout) -----------------------------
 int parse_blob(snb_ctx* c, const void* blob, size_t bytes) {
@@ -170,6 +170,48 @@ struct Builder {
     return c->planes == 2 && !(c->cfg.flags & SNB_FLAG_NO_TENSOR) && stride == 1 && cw.ks == 3 && cw.cin % 16 == 0 && cw.cout % 32 == 0;
   }
 
+  // device copy of the tcgen05 packing of one convolution's weights (made once, shared by every user)
+  const __half* tc_weights(const std::string& name, ConvW& cw) {
+    const int NT = 32;   // k_conv_tc / k_resblock_tc tile width (one packing)
+    if (!cw.w_tc.count(NT)) {
+      std::vector<__half> packed;
+      tc_pack_weights(c->wts[name + ".weight"].data.data(), cw.cout, cw.cin, cw.kz, NT, packed);
+      __half* dw = nullptr;
+      if (cudaMalloc(&dw, packed.size() * sizeof(__half)) != cudaSuccess) { fail = true; return nullptr; }
+      cudaMemcpy(dw, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice);
+      c->wallocs.push_back(dw);
+      cw.w_tc[NT] = dw;
+    }
+    return cw.w_tc[NT];
+  }
+
+  // out = ReLU(conv_b(ReLU(conv_a(in))) + res) with 32 channels, as ONE launch when the tcgen05 path allows it
+  bool block_fusable(const std::string& prefix, const Tens& in, int dil) const {
+    auto ia = c->convs.find(prefix + ".conv_a"), ib = c->convs.find(prefix + ".conv_b");
+    if (ia == c->convs.end() || ib == c->convs.end()) return false;
+    if (ia->second.cin != 32 || ia->second.cout != 32 || ib->second.cin != 32 || ib->second.cout != 32 || ia->second.kz != 1) return false;
+    return c->planes == 2 && !(c->cfg.flags & (SNB_FLAG_NO_TENSOR | SNB_FLAG_NO_FUSE)) && in.c == 32 && in.d == 1 && in.pad >= 2 * dil;
+  }
+  Tens resblock(const std::string& prefix, const Tens& in, int nmul, int dil, const Tens& res) {
+    auto ia = c->convs.find(prefix + ".conv_a"), ib = c->convs.find(prefix + ".conv_b");
+    if (ia == c->convs.end() || ib == c->convs.end()) { fail = true; snprintf(c->err, sizeof(c->err), "no weights for %s", prefix.c_str()); return Tens(); }
+    Tens out = alloc(nmul, 32, 1, in.h, in.w, in.pad);
+    RbPlan plan;
+    cudaError_t e = resblock_tc_plan(&plan, in, out, res, dil, c->num_sms);
+    if (e != cudaSuccess) { fail = true; snprintf(c->err, sizeof(c->err), "resblock_tc_plan(%s): %s", prefix.c_str(), cudaGetErrorString(e)); return out; }
+    const __half* wa = tc_weights(prefix + ".conv_a", ia->second);
+    const __half* wb = tc_weights(prefix + ".conv_b", ib->second);
+    const float* ba = ia->second.b; const float* bb = ib->second.b;
+    Op op; op.name = prefix + " [tc-block]";
+    const double px = (double)nmul * in.h * in.w;
+    op.flops = 2.0 * 2.0 * px * 32 * 32 * 9;
+    op.bytes = 4.0 * px * 32 * (&res == &in || res.p == in.p ? 2 : 3);
+    op.fn = [plan, nmul, wa, wb, ba, bb](int B, cudaStream_t st) { return launch_resblock_tc(plan, nmul * B, wa, wb, ba, bb, st); };
+    c->n_tc_convs += 2;
+    c->ops.push_back(op);
+    return out;
+  }
+
   Tens conv(const std::string& name, const Tens& in, int nmul, int stride, int dil, bool relu, const Tens* res) {
     auto it = c->convs.find(name);
     if (it == c->convs.end()) { fail = true; snprintf(c->err, sizeof(c->err), "no weights for %s", name.c_str()); return Tens(); }
@@ -184,17 +226,8 @@ struct Builder {
       TcConvPlan plan;
       cudaError_t e = tc_conv_plan(&plan, in, out, cw.cin, cw.cout, dil, cw.kz, c->num_sms);
       if (e != cudaSuccess) { fail = true; snprintf(c->err, sizeof(c->err), "tc_conv_plan(%s): %s", name.c_str(), cudaGetErrorString(e)); return out; }
-      const int NT = 32;   // k_conv_tc tile width (one packing)
-      if (!cw.w_tc.count(NT)) {
-        std::vector<__half> packed;
-        tc_pack_weights(c->wts[name + ".weight"].data.data(), cw.cout, cw.cin, cw.kz, NT, packed);
-        __half* dw = nullptr;
-        if (cudaMalloc(&dw, packed.size() * sizeof(__half)) != cudaSuccess) { fail = true; return out; }
-        cudaMemcpy(dw, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice);
-        c->wallocs.push_back(dw);
-        cw.w_tc[NT] = dw;
-      }
-      const __half* dw = cw.w_tc[NT];
+      const __half* dw = tc_weights(name, cw);
+      if (!dw) return out;
       const float* bias = cw.b;
       const bool has_res = res != nullptr;
       const Tens rt = res ? *res : Tens();
@@ -267,12 +300,17 @@ int build_plan(snb_ctx* c) {
     for (int bi = 0; bi < LAYER_BLOCKS[li - 1]; ++bi) {
       const std::string p = "backbone.layer" + std::to_string(li) + "." + std::to_string(bi);
       const int s = bi == 0 ? strides[li - 1] : 1, dil = li == 4 ? 2 : 1;
-      Tens a = b.conv(p + ".conv_a", x, 2, s, dil, true, nullptr);
       Tens sc = x;
       const bool ds = bi == 0 && li <= 3;
       if (ds) sc = b.conv(p + ".downsample", x, 2, s, 1, false, nullptr);
-      Tens o = b.conv(p + ".conv_b", a, 2, 1, dil, true, &sc);
-      b.free(a);
+      Tens o;
+      if (s == 1 && b.block_fusable(p, x, dil)) {
+        o = b.resblock(p, x, 2, dil, sc);
+      } else {
+        Tens a = b.conv(p + ".conv_a", x, 2, s, dil, true, nullptr);
+        o = b.conv(p + ".conv_b", a, 2, 1, dil, true, &sc);
+        b.free(a);
+      }
       if (ds) b.free(sc);
       if (!(li == 4 && bi == 0)) b.free(x);      // layer3's output stays alive for the gwc concat
       x = o;
@@ -352,9 +390,15 @@ int build_plan(snb_ctx* c) {
     Tens f = b.conv(p + ".conv_in", rin, 1, 1, 1, true, nullptr);
     for (int bi = 0; bi < 6; ++bi) {
       const std::string q = p + ".blocks." + std::to_string(bi);
-      Tens a = b.conv(q + ".conv_a", f, 1, 1, REF_DIL[bi], true, nullptr);
-      Tens o = b.conv(q + ".conv_b", a, 1, 1, REF_DIL[bi], true, &f);
-      b.free(a); b.free(f); f = o;
+      Tens o;
+      if (b.block_fusable(q, f, REF_DIL[bi])) {
+        o = b.resblock(q, f, 1, REF_DIL[bi], f);
+      } else {
+        Tens a = b.conv(q + ".conv_a", f, 1, 1, REF_DIL[bi], true, nullptr);
+        o = b.conv(q + ".conv_b", a, 1, 1, REF_DIL[bi], true, &f);
+        b.free(a);
+      }
+      b.free(f); f = o;
     }
     b.tap("refine" + std::to_string(s) + ".feat", f, 1);
     Plane nd = b.conv_to1(p + ".conv_out", f, 1, true, &rin);
