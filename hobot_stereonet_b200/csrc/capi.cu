@@ -331,11 +331,13 @@ int64_t snb_debug_read(snb_ctx* c, const char* name, float* dst, uint64_t cap, i
   const size_t slice = t.slice();
   const int ws = t.ws(), pad = t.pad;
   // element (nn, hl, ch, dd, y, x) of the padded C8 layout
+  const size_t ss = t.sample_stride(), lo = t.lo_off();
+  const size_t span = (size_t)(N - 1) * ss + (t.planes - 1) * lo + (size_t)t.cb * t.d * slice;   // sub-views included
   auto at = [&](int nn, int hl, int ch, int dd, int y, int x) {
-    return ((((size_t)(nn * t.planes + hl) * t.cb + ch / 8) * t.d + dd) * slice) + ((size_t)(y + pad) * ws + x + pad) * 8 + ch % 8;
+    return (size_t)nn * ss + (size_t)hl * lo + ((size_t)(ch / 8) * t.d + dd) * slice + ((size_t)(y + pad) * ws + x + pad) * 8 + ch % 8;
   };
   if (t.planes == 2) {
-    std::vector<__half> tmp((size_t)N * 2 * t.cb * t.d * slice);
+    std::vector<__half> tmp(span);
     CK(c, cudaMemcpy(tmp.data(), t.p, tmp.size() * 2, cudaMemcpyDeviceToHost));
     for (int nn = 0; nn < N; ++nn)
       for (int ch = 0; ch < t.c; ++ch) {
@@ -347,7 +349,7 @@ int64_t snb_debug_read(snb_ctx* c, const char* name, float* dst, uint64_t cap, i
       }
     return (int64_t)n;
   }
-  std::vector<float> tmp((size_t)N * t.cb * t.d * slice);
+  std::vector<float> tmp(span);
   CK(c, cudaMemcpy(tmp.data(), t.p, tmp.size() * 4, cudaMemcpyDeviceToHost));
   for (int nn = 0; nn < N; ++nn)
     for (int ch = 0; ch < t.c; ++ch) {

@@ -31,6 +31,7 @@ struct Tens {            // C8 activation tensor
   int c = 0;             // logical channels (<= cb*8)
   int planes = 1;
   int pad = 0;
+  int pcb = 0;           // channel blocks of the parent allocation when this is a channel sub-view (0: owns its memory)
   int hs() const { return h + 2 * pad; }
   int ws() const { return w + 2 * pad; }
   float* f() const { return static_cast<float*>(p); }
@@ -38,7 +39,7 @@ struct Tens {            // C8 activation tensor
   size_t esize() const { return planes == 2 ? 2 : 4; }
   size_t slice() const { return (size_t)hs() * ws() * 8; }                 // one (cb, d) slice, elements
   size_t org() const { return ((size_t)pad * ws() + pad) * 8; }            // interior pixel (0,0) inside a slice
-  size_t plane_elems() const { return (size_t)cb * d * slice(); }          // one (n[,hl]) slab
+  size_t plane_elems() const { return (size_t)(pcb ? pcb : cb) * d * slice(); }   // one (n[,hl]) slab
   size_t sample_stride() const { return plane_elems() * planes; }          // elements between samples
   size_t lo_off() const { return planes == 2 ? plane_elems() : 0; }
   size_t elems() const { return (size_t)n * cb * d * slice(); }
@@ -52,6 +53,14 @@ struct TV {
   size_t ss = 0, lo = 0, slice = 0;
   int ws = 0;
 };
+// channel blocks [cb0, cb0 + ncb) of t as a tensor of its own (same strides, no copy)
+inline Tens sub_view(const Tens& t, int cb0, int ncb) {
+  Tens s = t;
+  s.p = static_cast<char*>(t.p) + (size_t)cb0 * t.d * t.slice() * t.esize();
+  s.pcb = t.pcb ? t.pcb : t.cb;
+  s.cb = ncb; s.c = ncb * 8;
+  return s;
+}
 inline TV view(const Tens& t) {
   TV v;
   v.p = static_cast<char*>(t.p) + t.org() * t.esize();

@@ -305,9 +305,14 @@ cudaError_t tc_conv_plan(TcConvPlan* plan, const Tens& in, const Tens& out, int 
   p.in_pad = in.pad;
   p.ccs = cout / TC_NT;
   p.tiles_x = cdiv(p.W, 128);
-  // 6 output rows per tile (8 input rows, 1.33x halo) when that still fills the GPU, else 2 rows for parallelism
+  // tile height: minimise waves x input rows per tile (R + 2 rows are staged and multiplied for R output rows)
   auto tiles_for = [&](int R) { return (long)in.n * p.D * cdiv(p.H, R * dil) * dil * p.tiles_x * p.ccs; };
-  const int R = tiles_for(6) >= num_sms ? 6 : 2;
+  int R = 6;
+  long best = -1;
+  for (int r : {6, 4, 2}) {
+    const long cost = ((tiles_for(r) + num_sms - 1) / num_sms) * (r + 2);
+    if (best < 0 || cost < best) { best = cost; R = r; }
+  }
   const int ns = tc_layout(p, R);
   if (ns < 1) return cudaErrorInvalidValue;
   p.nstages = ns;
@@ -342,6 +347,7 @@ cudaError_t launch_conv_tc(const TcConvPlan& plan, int N, const void* w, const f
   if (prof) cudaMemsetAsync(d_prof, 0, 256 * 16 * sizeof(long long), st);
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   if (p.R == 6) launch_r<6>(p, grid, plan.smem, st);
+  else if (p.R == 4) launch_r<4>(p, grid, plan.smem, st);
   else launch_r<2>(p, grid, plan.smem, st);
   if (prof) {     // diagnostics only: synchronous read-back, max over CTAs of each role's counters
     cudaStreamSynchronize(st);

@@ -160,7 +160,7 @@ struct Builder {
     if (!p.p) fail = true;
     return p;
   }
-  void free(const Tens& t) { c->arena.put(t.p); }
+  void free(const Tens& t) { if (!t.pcb) c->arena.put(t.p); }    // sub-views do not own memory
   void free(const Plane& p) { c->arena.put(p.p); }
   void tap(const std::string& name, const Tens& t, int nmul) { Stage s; s.t = t; s.nmul = nmul; c->stages[name] = s; }
   void tap(const std::string& name, const Plane& p) { Stage s; s.is_plane = true; s.p = p; c->stages[name] = s; }
@@ -212,12 +212,13 @@ struct Builder {
     return out;
   }
 
-  Tens conv(const std::string& name, const Tens& in, int nmul, int stride, int dil, bool relu, const Tens* res) {
+  Tens conv(const std::string& name, const Tens& in, int nmul, int stride, int dil, bool relu, const Tens* res,
+            const Tens* dst = nullptr) {
     auto it = c->convs.find(name);
     if (it == c->convs.end()) { fail = true; snprintf(c->err, sizeof(c->err), "no weights for %s", name.c_str()); return Tens(); }
     ConvW& cw = it->second;
     const int ho = (in.h + stride - 1) / stride, wo = (in.w + stride - 1) / stride;
-    Tens out = alloc(nmul, cw.cout, in.d, ho, wo, in.pad);
+    Tens out = dst ? *dst : alloc(nmul, cw.cout, in.d, ho, wo, in.pad);
     Op op; op.name = name;
     const double px = (double)nmul * in.d * ho * wo;
     op.flops = 2.0 * px * cw.cout * cw.cin * cw.ks * cw.ks * cw.kz;
@@ -295,6 +296,9 @@ int build_plan(snb_ctx* c) {
   x = b.conv("backbone.firstconv.2", y, 2, 2, 1, true, nullptr); b.free(y);
   b.tap("firstconv", x, 2);
   const int strides[4] = {1, K >= 3 ? 2 : 1, K >= 4 ? 2 : 1, 1};
+  // gwc feature = cat(layer3, layer4) along channels, [2B][32][h][w][8]: the last block of each layer writes its half
+  Tens gwc = b.alloc(2, 256, 1, h, w, PAD_BACKBONE);
+  const Tens gwc_l3 = sub_view(gwc, 0, 16), gwc_l4 = sub_view(gwc, 16, 16);
   Tens l3, l4;
   for (int li = 1; li <= 4; ++li) {
     for (int bi = 0; bi < LAYER_BLOCKS[li - 1]; ++bi) {
@@ -307,12 +311,14 @@ int build_plan(snb_ctx* c) {
       if (s == 1 && b.block_fusable(p, x, dil)) {
         o = b.resblock(p, x, 2, dil, sc);
       } else {
+        const bool last = bi == LAYER_BLOCKS[li - 1] - 1;
+        const Tens* dst = (li == 3 && last) ? &gwc_l3 : (li == 4 && last) ? &gwc_l4 : nullptr;
         Tens a = b.conv(p + ".conv_a", x, 2, s, dil, true, nullptr);
-        o = b.conv(p + ".conv_b", a, 2, 1, dil, true, &sc);
+        o = b.conv(p + ".conv_b", a, 2, 1, dil, true, &sc, dst);
         b.free(a);
       }
       if (ds) b.free(sc);
-      if (!(li == 4 && bi == 0)) b.free(x);      // layer3's output stays alive for the gwc concat
+      b.free(x);
       x = o;
     }
     b.tap("layer" + std::to_string(li), x, 2);
@@ -320,23 +326,6 @@ int build_plan(snb_ctx* c) {
     if (li == 4) l4 = x;
   }
   (void)LAYER_CH;
-  // gwc feature = cat(layer3, layer4) along channels: [2B][32][h][w][8]
-  Tens gwc = b.alloc(2, 256, 1, h, w, PAD_BACKBONE);
-  {
-    Op op; op.name = "gwc_concat";
-    // one row per (sample[, hi/lo plane]): 16 blocks from each source into a 32-block row
-    const int planes = c->planes;
-    const size_t half = 16 * l3.slice() * l3.esize();     // 16 channel blocks incl. their zero borders
-    char* dst = static_cast<char*>(gwc.p); const void* s3 = l3.p; const void* s4 = l4.p;
-    op.fn = [=](int B, cudaStream_t st) {
-      cudaError_t e = cudaMemcpy2DAsync(dst, 2 * half, s3, half, half, 2 * B * planes, cudaMemcpyDeviceToDevice, st);
-      if (e != cudaSuccess) return e;
-      return cudaMemcpy2DAsync(dst + half, 2 * half, s4, half, half, 2 * B * planes, cudaMemcpyDeviceToDevice, st);
-    };
-    op.bytes = 4.0 * (double)16 * h * w * 8 * 4;
-    c->ops.push_back(op);
-  }
-  b.free(l3); b.free(l4);
   b.tap("gwc", gwc, 2);
   Tens lc = b.conv("backbone.lastconv.0", gwc, 2, 1, 1, true, nullptr);
   Tens cat = b.conv("backbone.lastconv.1", lc, 2, 1, 1, false, nullptr); b.free(lc);
