@@ -102,6 +102,7 @@ struct TcConvParams {    // k_conv_tc.cu
   int N, D, H, W, CBin, CBout;
   int dil, kz, relu;
   int nk16;              // Cin / 16
+  int cin8;              // 1: Cin <= 8 (one channel block): K = 16 is two adjacent taps x 8 channels (A LBO = one pixel)
   int R;                 // output rows per tile (template instance)
   int BW, BH;            // shared-memory tile: pixels per row, input rows per stage (R + 2)
   int in_pad;            // zero border of the input tensor (rows below H + in_pad are never read)

@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcConvParams p)
     // ================================ bulk-copy producer ================================
     const __half* in = static_cast<const __half*>(p.in.p);
     const uint32_t row_bytes = (uint32_t)p.BW * 16;
+    const int npc = p.cin8 ? 2 : 4;                                // (plane, chunk) regions per stage
     uint32_t it = 0;
     long long w_empty = 0, t_start = clock64();
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -107,23 +108,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcConvParams p)
             const long long c0 = clock64();
             mbar_wait(&empty[slot], ((it / p.nstages) & 1) ^ 1);
             w_empty += clock64() - c0;
-            mbar_expect_tx(&full[slot], (p.dbg & 1) ? 0u : 4u * nrows * row_bytes + TC_W_BYTES);
+            mbar_expect_tx(&full[slot], (p.dbg & 1) ? 0u : (uint32_t)npc * nrows * row_bytes + p.w_bytes);
           }
           __syncwarp();
           ++it;
           if (p.dbg & 1) continue;
-          for (int i = lane; i < 4 * BH; i += 32) {
-            const int pc = i / BH, j = i - pc * BH;          // pc = plane*2 + chunk
+          for (int i = lane; i < npc * BH; i += 32) {
+            const int pc = i / BH, j = i - pc * BH;          // pc = plane*2 + chunk (cin8: pc = plane, one chunk)
             if (j >= nrows) continue;
             const int y = y0 + j * p.dil;
-            const __half* src = in + (size_t)tc.n * p.in.ss + (size_t)(pc >> 1) * p.in.lo +
-                                ((size_t)(k16 * 2 + (pc & 1)) * p.D + zin) * p.in.slice +
+            const int plane = p.cin8 ? pc : pc >> 1, cb = p.cin8 ? 0 : k16 * 2 + (pc & 1);
+            const __half* src = in + (size_t)tc.n * p.in.ss + (size_t)plane * p.in.lo +
+                                ((size_t)cb * p.D + zin) * p.in.slice +
                                 ((ptrdiff_t)y * p.in.ws + (x0 - p.dil)) * 8;
             bulk_load(sa + (size_t)pc * p.a_chunk_bytes + (size_t)j * row_bytes, src, row_bytes, &full[slot]);
           }
           if (lane == 0) {
-            const __half* wsrc = p.w + (((size_t)tc.cc * p.nk16 + k16) * p.kz + dz) * (size_t)(TC_W_BYTES / 2);
-            bulk_load(sa + 4 * (size_t)p.a_chunk_bytes, wsrc, TC_W_BYTES, &full[slot]);
+            const __half* wsrc = p.w + (((size_t)tc.cc * p.nk16 + k16) * p.kz + dz) * (size_t)(p.w_bytes / 2);
+            bulk_load(sa + (size_t)npc * p.a_chunk_bytes, wsrc, p.w_bytes, &full[slot]);
           }
         }
       }
@@ -150,9 +152,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcConvParams p)
           ++it;
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)slot * p.stage_bytes);
-          const uint64_t da_hi = make_smem_desc(sa, a_lbo, 128);
-          const uint64_t da_lo = make_smem_desc(sa + 2 * p.a_chunk_bytes, a_lbo, 128);
-          const uint64_t db = make_smem_desc(sa + 4 * p.a_chunk_bytes, b_lbo, 128);
+          // cin8: the second K half of an MMA is the NEXT tap's pixel (LBO = dil pixels), one chunk per plane
+          const uint64_t da_hi = make_smem_desc(sa, p.cin8 ? dil16 * 16 : a_lbo, 128);
+          const uint64_t da_lo = make_smem_desc(sa + (p.cin8 ? 1 : 2) * p.a_chunk_bytes, p.cin8 ? dil16 * 16 : a_lbo, 128);
+          const uint64_t db = make_smem_desc(sa + (p.cin8 ? 2 : 4) * p.a_chunk_bytes, b_lbo, 128);
           constexpr uint32_t KX_B = 2 * TC_SLOT_COLS;                // 16-byte units between the kx weight blocks
 #pragma unroll
           for (int j = 0; j < BH; ++j, ++rs) {
@@ -162,7 +165,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcConvParams p)
             if (leader) {
               const uint32_t dcol = tmem_base + ts * TC_SLOT_COLS;
               const uint64_t a_hi = da_hi + (uint64_t)(j * row16), a_lo = da_lo + (uint64_t)(j * row16);
-              if (!(p.dbg & 2)) {
+              if (p.cin8) {                      // taps (kx0, kx1) then (kx2, zero weights)
+                umma_f16_zero(dcol, a_hi, db, idesc1);
+                umma_f16_acc(dcol + TC_SLOT_COLS / 2, a_lo, db, idesc2);
+                umma_f16_acc(dcol, a_hi + 2 * dil16, db + KX_B, idesc1);
+                umma_f16_acc(dcol + TC_SLOT_COLS / 2, a_lo + 2 * dil16, db + KX_B, idesc2);
+              } else if (!(p.dbg & 2)) {
                 umma_f16_zero(dcol, a_hi, db, idesc1);
                 umma_f16_acc(dcol + TC_SLOT_COLS / 2, a_lo, db, idesc2);
                 umma_f16_acc(dcol, a_hi + dil16, db + KX_B, idesc1);
@@ -285,11 +293,11 @@ static const int SMEM_BUDGET = 227 * 1024 - 1024;
 
 static int tc_layout(TcConvParams& p, int R) {
   p.R = R;
-  p.BW = 128 + 2 * p.dil;
+  p.BW = 128 + (p.cin8 ? 3 : 2) * p.dil;       // cin8: the zero-weight half of the last tap pair reads one tap further
   p.BH = R + 2;
   p.a_chunk_bytes = (uint32_t)(p.BH * p.BW * 16);
-  p.w_bytes = TC_W_BYTES;
-  p.stage_bytes = (4 * p.a_chunk_bytes + p.w_bytes + 127) / 128 * 128;
+  p.w_bytes = p.cin8 ? TC_W_BYTES * 2 / 3 : TC_W_BYTES;
+  p.stage_bytes = ((p.cin8 ? 2 : 4) * p.a_chunk_bytes + p.w_bytes + 127) / 128 * 128;
   const int fixed = 128 + (2 * 8 + 4) * 8 + 16;
   int ns = (SMEM_BUDGET - fixed) / (int)p.stage_bytes;
   return ns > 4 ? 4 : ns;
@@ -297,11 +305,13 @@ static int tc_layout(TcConvParams& p, int R) {
 
 // Chooses the tile height / pipeline depth for one convolution.  in: split-fp16 tensor with pad >= dil.
 cudaError_t tc_conv_plan(TcConvPlan* plan, const Tens& in, const Tens& out, int cin, int cout, int dil, int kz, int num_sms) {
-  if (cin % 16 || cout % TC_NT || in.planes != 2 || out.planes != 2 || in.pad < dil) return cudaErrorInvalidValue;
+  const bool cin8 = cin <= 8 && in.cb == 1 && kz == 1;
+  if ((!cin8 && cin % 16) || cout % TC_NT || in.planes != 2 || out.planes != 2 || in.pad < dil) return cudaErrorInvalidValue;
   *plan = TcConvPlan();
   TcConvParams& p = plan->p;
   p.in = view(in); p.out = view(out);
-  p.D = in.d; p.H = in.h; p.W = in.w; p.CBin = cin / 8; p.CBout = cout / 8; p.dil = dil; p.kz = kz; p.nk16 = cin / 16;
+  p.cin8 = cin8 ? 1 : 0;
+  p.D = in.d; p.H = in.h; p.W = in.w; p.CBin = cin8 ? 1 : cin / 8; p.CBout = cout / 8; p.dil = dil; p.kz = kz; p.nk16 = cin8 ? 1 : cin / 16;
   p.in_pad = in.pad;
   p.ccs = cout / TC_NT;
   p.tiles_x = cdiv(p.W, 128);
@@ -367,7 +377,25 @@ cudaError_t launch_conv_tc(const TcConvPlan& plan, int N, const void* w, const f
 // [Cout][Cin][kz][3][3] fp32; row = part*96 + half*48 + ky*16 + (co % 16), part 0 = W_hi, 1 = W_lo,
 // half = which 16 of the tile's 32 channels (one epilogue warp set each).
 void tc_pack_weights(const float* W, int cout, int cin, int kz, int NT, std::vector<__half>& out) {
-  (void)NT;
+  if (NT == 8) {
+    // cin8 packing: [cc][tap pair g][K half = kx - 2g][192 rows][8 ch]; the half of pair 1 that would be kx = 3 stays zero
+    const int ccs = cout / TC_NT;
+    out.assign((size_t)ccs * 2 * 2 * TC_SLOT_COLS * 8, __float2half(0.f));
+    for (int co = 0; co < cout; ++co)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int ky = 0; ky < 3; ++ky)
+          for (int kx = 0; kx < 3; ++kx) {
+            const float v = W[(((size_t)co * cin + ci) * 3 + ky) * 3 + kx];
+            const __half hi = __float2half_rn(v);
+            const __half lo = __float2half_rn(v - __half2float(hi));
+            const int cc = co / TC_NT, cl = co % TC_NT;
+            const int row = (cl / 16) * 48 + ky * 16 + cl % 16;
+            const size_t blk = ((size_t)cc * 2 + kx / 2) * 2 + kx % 2;
+            out[(blk * TC_SLOT_COLS + row) * 8 + ci] = hi;
+            out[(blk * TC_SLOT_COLS + 96 + row) * 8 + ci] = lo;
+          }
+    return;
+  }
   const int ccs = cout / TC_NT, nk16 = cin / 16;
   out.assign((size_t)ccs * nk16 * kz * 3 * 2 * TC_SLOT_COLS * 8, __float2half(0.f));
   for (int co = 0; co < cout; ++co)

@@ -167,12 +167,12 @@ struct Builder {
 
   // tcgen05 path: stride-1 3x3 / 3x3x3 convolutions with Cin % 16 == 0 and Cout % 32 == 0
   bool tc_eligible(const ConvW& cw, int stride) const {
-    return c->planes == 2 && !(c->cfg.flags & SNB_FLAG_NO_TENSOR) && stride == 1 && cw.ks == 3 && cw.cin % 16 == 0 && cw.cout % 32 == 0;
+    return c->planes == 2 && !(c->cfg.flags & SNB_FLAG_NO_TENSOR) && stride == 1 && cw.ks == 3 && (cw.cin % 16 == 0 || (cw.cin <= 8 && cw.kz == 1)) && cw.cout % 32 == 0;
   }
 
   // device copy of the tcgen05 packing of one convolution's weights (made once, shared by every user)
   const __half* tc_weights(const std::string& name, ConvW& cw) {
-    const int NT = 32;   // k_conv_tc / k_resblock_tc tile width (one packing)
+    const int NT = cw.cin <= 8 ? 8 : 32;   // packing id: 32 = 16-channel K chunks, 8 = "cin8" tap-pair packing
     if (!cw.w_tc.count(NT)) {
       std::vector<__half> packed;
       tc_pack_weights(c->wts[name + ".weight"].data.data(), cw.cout, cw.cin, cw.kz, NT, packed);
