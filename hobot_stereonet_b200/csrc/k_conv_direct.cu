@@ -14,6 +14,8 @@ namespace snb {
 
 template <int COT, typename T>
 __global__ void __launch_bounds__(256) k_conv_direct(ConvParams p) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int CO = 4 * COT;               // output channels per CTA
   extern __shared__ float smem[];
   const int pad = p.dil * (p.ks / 2);
@@ -167,10 +169,10 @@ cudaError_t launch_conv_direct(ConvParams p, int cout, cudaStream_t st) {
     const dim3 g(tiles, cout / 32, p.N * p.Dout);
     if (p.half) {
       if (need_attr(3)) cudaFuncSetAttribute(k_conv_direct<8, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      k_conv_direct<8, __half><<<g, 256, sm, st>>>(p);
+      launch_k(k_conv_direct<8, __half>, g, 256, sm, st, p);
     } else {
       if (need_attr(0)) cudaFuncSetAttribute(k_conv_direct<8, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      k_conv_direct<8, float><<<g, 256, sm, st>>>(p);
+      launch_k(k_conv_direct<8, float>, g, 256, sm, st, p);
     }
   } else if (cout % 16 == 0) {
     size_t sm = conv_direct_smem(p, 16);
@@ -178,10 +180,10 @@ cudaError_t launch_conv_direct(ConvParams p, int cout, cudaStream_t st) {
     const dim3 g(tiles, cout / 16, p.N * p.Dout);
     if (p.half) {
       if (need_attr(4)) cudaFuncSetAttribute(k_conv_direct<4, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      k_conv_direct<4, __half><<<g, 256, sm, st>>>(p);
+      launch_k(k_conv_direct<4, __half>, g, 256, sm, st, p);
     } else {
       if (need_attr(1)) cudaFuncSetAttribute(k_conv_direct<4, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      k_conv_direct<4, float><<<g, 256, sm, st>>>(p);
+      launch_k(k_conv_direct<4, float>, g, 256, sm, st, p);
     }
   } else {
     return cudaErrorInvalidValue;
@@ -192,6 +194,8 @@ cudaError_t launch_conv_direct(ConvParams p, int cout, cudaStream_t st) {
 // ---- Cout = 1: one thread per output element, weights in shared memory --------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) k_conv_to1(ConvTo1Params p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_w[];            // [CBin][kz][9][8]
   const int nw = p.CBin * p.kz * 9 * 8;
   for (int i = threadIdx.x; i < nw; i += blockDim.x) s_w[i] = __ldg(p.w + i);
@@ -237,8 +241,8 @@ __global__ void __launch_bounds__(256) k_conv_to1(ConvTo1Params p) {
 cudaError_t launch_conv_to1(const ConvTo1Params& p, cudaStream_t st) {
   const size_t sm = (size_t)p.CBin * p.kz * 9 * 8 * sizeof(float);
   const dim3 g(cdiv(p.W, 32), cdiv(p.H, 8), p.N * p.D);
-  if (p.half) k_conv_to1<__half><<<g, 256, sm, st>>>(p);
-  else k_conv_to1<float><<<g, 256, sm, st>>>(p);
+  if (p.half) launch_k(k_conv_to1<__half>, g, 256, sm, st, p);
+  else launch_k(k_conv_to1<float>, g, 256, sm, st, p);
   return cudaGetLastError();
 }
 

@@ -82,6 +82,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcConvParams p)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_trigger();          // the next kernel may start its prologue
+  pdl_wait();             // everything above touched only shared memory / TMEM
   const uint32_t tmem_base = *tmem_slot;
   const int zpad = p.kz >> 1;
 
@@ -340,7 +342,7 @@ static void launch_r(const TcConvParams& p, int grid, size_t smem, cudaStream_t 
     cudaFuncSetAttribute(k_conv_tc<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_done[dev & 31] = true;
   }
-  k_conv_tc<R><<<grid, TC_THREADS, smem, st>>>(p);
+  launch_k(k_conv_tc<R>, grid, TC_THREADS, smem, st, p);
 }
 
 cudaError_t launch_conv_tc(const TcConvPlan& plan, int N, const void* w, const float* bias, const Tens* res, int relu,

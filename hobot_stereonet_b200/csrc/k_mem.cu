@@ -12,6 +12,8 @@ namespace snb {
 // gives its input: value = s8 * (1/128) (preprocess.cpp:1037), channels 0-2 left, 3-5 right.
 template <typename T>
 __global__ void k_pre_s8(const int8_t* __restrict__ s8, TV img, int B, int H, int W, int Hp, int Wp) {
+  pdl_trigger();
+  pdl_wait();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int n = blockIdx.z;                  // 0..2B-1
@@ -30,8 +32,8 @@ __global__ void k_pre_s8(const int8_t* __restrict__ s8, TV img, int B, int H, in
 
 cudaError_t launch_pre_s8(const int8_t* s8, Tens img, int B, int H, int W, cudaStream_t st) {
   const dim3 g(cdiv(img.w, 128), img.h, 2 * B);
-  if (img.planes == 2) k_pre_s8<__half><<<g, 128, 0, st>>>(s8, view(img), B, H, W, img.h, img.w);
-  else k_pre_s8<float><<<g, 128, 0, st>>>(s8, view(img), B, H, W, img.h, img.w);
+  if (img.planes == 2) launch_k(k_pre_s8<__half>, g, 128, 0, st, s8, view(img), B, H, W, img.h, img.w);
+  else launch_k(k_pre_s8<float>, g, 128, 0, st, s8, view(img), B, H, W, img.h, img.w);
   return cudaGetLastError();
 }
 
@@ -42,6 +44,8 @@ cudaError_t launch_pre_s8(const int8_t* s8, Tens img, int B, int H, int W, cudaS
 template <typename T>
 __global__ void k_pre_nv12(const uint8_t* __restrict__ frames, TV img, int8_t* __restrict__ s8, int B, int H, int W, int Hp,
                            int Wp, int correct) {
+  pdl_trigger();
+  pdl_wait();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int n = blockIdx.z;
@@ -81,9 +85,9 @@ cudaError_t launch_pre_nv12(const uint8_t* frames, Tens img, int8_t* s8, int B, 
                             cudaStream_t st) {
   const dim3 g(cdiv(img.w, 128), img.h, 2 * B);
   if (img.planes == 2)
-    k_pre_nv12<__half><<<g, 128, 0, st>>>(frames, view(img), s8, B, H, W, img.h, img.w, correct);
+    launch_k(k_pre_nv12<__half>, g, 128, 0, st, frames, view(img), s8, B, H, W, img.h, img.w, correct);
   else
-    k_pre_nv12<float><<<g, 128, 0, st>>>(frames, view(img), s8, B, H, W, img.h, img.w, correct);
+    launch_k(k_pre_nv12<float>, g, 128, 0, st, frames, view(img), s8, B, H, W, img.h, img.w, correct);
   return cudaGetLastError();
 }
 
@@ -102,6 +106,8 @@ struct CostvolParams {
 
 template <typename T>
 __global__ void __launch_bounds__(256) k_costvol(CostvolParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   const int y = blockIdx.x, b = blockIdx.y, q = blockIdx.z;    // q in 0..3
   const int w = p.w, h = p.h, D = p.D;
@@ -155,10 +161,10 @@ cudaError_t launch_costvol(Tens gwc, Tens cat, Tens vol, int B, int D, cudaStrea
   CostvolParams p{view(gwc), view(cat), view(vol), B, D, h, w};
   if (vol.planes == 2) {
     if (need_attr(5)) cudaFuncSetAttribute(k_costvol<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    k_costvol<__half><<<dim3(h, B, 4), 256, smem, st>>>(p);
+    launch_k(k_costvol<__half>, dim3(h, B, 4), 256, smem, st, p);
   } else {
     if (need_attr(2)) cudaFuncSetAttribute(k_costvol<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    k_costvol<float><<<dim3(h, B, 4), 256, smem, st>>>(p);
+    launch_k(k_costvol<float>, dim3(h, B, 4), 256, smem, st, p);
   }
   return cudaGetLastError();
 }
@@ -166,6 +172,8 @@ cudaError_t launch_costvol(Tens gwc, Tens cat, Tens vol, int B, int D, cudaStrea
 // ------------------------------------------------------------------------------------------------
 // M4 softmax over D + soft-argmin, online (single pass over the cost column), fp32 throughout.
 __global__ void k_softargmin(const float* __restrict__ cost, float* __restrict__ disp, int D, int hw, float invD) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (i >= hw) return;
@@ -186,7 +194,7 @@ __global__ void k_softargmin(const float* __restrict__ cost, float* __restrict__
 
 cudaError_t launch_softargmin(Plane cost, Plane disp, cudaStream_t st) {
   const int hw = cost.h * cost.w;
-  k_softargmin<<<dim3(cdiv(hw, 128), cost.n), 128, 0, st>>>(cost.p, disp.p, cost.d, hw, 1.0f / cost.d);
+  launch_k(k_softargmin, dim3(cdiv(hw, 128), cost.n), 128, 0, st, cost.p, disp.p, cost.d, hw, 1.0f / cost.d);
   return cudaGetLastError();
 }
 
@@ -195,6 +203,8 @@ cudaError_t launch_softargmin(Plane cost, Plane disp, cudaStream_t st) {
 // left image bilinearly resized to the stage resolution (integer factor f: mean of the central 2x2).
 template <typename T>
 __global__ void k_refine_in(const float* __restrict__ disp, TV img, TV out, int h, int w, int f) {
+  pdl_trigger();
+  pdl_wait();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y, b = blockIdx.z;
   const int W2 = 2 * w;
@@ -230,8 +240,8 @@ __global__ void k_refine_in(const float* __restrict__ disp, TV img, TV out, int 
 cudaError_t launch_refine_in(Plane disp, Tens img_full, Tens out, int B, cudaStream_t st) {
   const int f = img_full.h / out.h;
   const dim3 g(cdiv(out.w, 128), out.h, B);
-  if (out.planes == 2) k_refine_in<__half><<<g, 128, 0, st>>>(disp.p, view(img_full), view(out), disp.h, disp.w, f);
-  else k_refine_in<float><<<g, 128, 0, st>>>(disp.p, view(img_full), view(out), disp.h, disp.w, f);
+  if (out.planes == 2) launch_k(k_refine_in<__half>, g, 128, 0, st, disp.p, view(img_full), view(out), disp.h, disp.w, f);
+  else launch_k(k_refine_in<float>, g, 128, 0, st, disp.p, view(img_full), view(out), disp.h, disp.w, f);
   return cudaGetLastError();
 }
 
@@ -240,6 +250,8 @@ cudaError_t launch_refine_in(Plane disp, Tens img_full, Tens out, int B, cudaStr
 // from the padded map; q = rint(dn * qmul) so that q * 2.60443857769133e-06 * 192 = pixels.
 __global__ void k_post_quant(const float* __restrict__ disp, int32_t* __restrict__ out, int H, int W, int Hp, int Wp,
                              float qmul) {
+  pdl_trigger();
+  pdl_wait();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y, b = blockIdx.z;
   if (x >= W) return;
@@ -247,7 +259,7 @@ __global__ void k_post_quant(const float* __restrict__ disp, int32_t* __restrict
 }
 
 cudaError_t launch_post_quant(Plane disp, int32_t* out, int H, int W, float qmul, cudaStream_t st) {
-  k_post_quant<<<dim3(cdiv(W, 128), H, disp.n), 128, 0, st>>>(disp.p, out, H, W, disp.h, disp.w, qmul);
+  launch_k(k_post_quant, dim3(cdiv(W, 128), H, disp.n), 128, 0, st, disp.p, out, H, W, disp.h, disp.w, qmul);
   return cudaGetLastError();
 }
 

@@ -123,6 +123,10 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
     for (int i = 0; i < RB_ASLOTS; ++i) { mbar_init(&sa_full[i], 1); mbar_init(&sa_empty[i], RB_GROUP_WARPS); }
     for (int i = 0; i < RB_BSLOTS; ++i) { mbar_init(&sb_full[i], 1); mbar_init(&sb_empty[i], RB_GROUP_WARPS); }
     fence_barrier_init();
+    // weights are constants of the pass: stage them before waiting on the previous kernel
+    mbar_expect_tx(w_full, 2 * RB_W_BYTES);
+    bulk_load(s_wa, p.wa, RB_W_BYTES, w_full);
+    bulk_load(s_wb, p.wb, RB_W_BYTES, w_full);
   }
   if (warp == 1) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
   if (threadIdx.x >= 64 && threadIdx.x < 128) s_bias[threadIdx.x - 64] = threadIdx.x < 96 ? p.ba[threadIdx.x - 64] : p.bb[threadIdx.x - 96];
@@ -133,6 +137,8 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_trigger();          // the next kernel may start its prologue
+  pdl_wait();             // everything above touched only shared memory / TMEM / constant weights
   const uint32_t tmem_base = tmem_slot;
   const int d = p.dil;
   long long t_start = 0, tw0 = 0, tw1 = 0, tw2 = 0, tw3 = 0;
@@ -141,11 +147,6 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
 
   if (warp == 0) {
     // ================================ bulk-copy producer ================================
-    if (lane == 0) {
-      mbar_expect_tx(w_full, 2 * RB_W_BYTES);
-      bulk_load(s_wa, p.wa, RB_W_BYTES, w_full);
-      bulk_load(s_wb, p.wb, RB_W_BYTES, w_full);
-    }
     const __half* in = static_cast<const __half*>(p.in.p);
     uint32_t itx = 0;
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
@@ -424,7 +425,7 @@ cudaError_t launch_resblock_tc(const RbPlan& plan, int N, const void* wa, const 
   const int grid = p.total_units < plan.num_sms ? p.total_units : plan.num_sms;
   static const int prof = getenv("SNB_TC_PROF") ? atoi(getenv("SNB_TC_PROF")) : 0;
   if (!prof) {
-    k_resblock_tc<false><<<grid, RB_THREADS, plan.smem, st>>>(p);
+    launch_k(k_resblock_tc<false>, grid, RB_THREADS, plan.smem, st, p);
     return cudaGetLastError();
   }
   // diagnostics only: per-role cycle counters, synchronous read-back, max over CTAs
@@ -432,7 +433,7 @@ cudaError_t launch_resblock_tc(const RbPlan& plan, int N, const void* wa, const 
   if (!d_prof) cudaMalloc(&d_prof, 256 * 24 * sizeof(long long));
   p.prof = d_prof;
   cudaMemsetAsync(d_prof, 0, 256 * 24 * sizeof(long long), st);
-  k_resblock_tc<true><<<grid, RB_THREADS, plan.smem, st>>>(p);
+  launch_k(k_resblock_tc<true>, grid, RB_THREADS, plan.smem, st, p);
   cudaStreamSynchronize(st);
   std::vector<long long> h(grid * 24);
   cudaMemcpy(h.data(), d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
