@@ -129,6 +129,18 @@ struct RbParams {        // k_resblock_tc.cu: fused 32-channel residual block
 };
 struct RbPlan { RbParams p; size_t smem; int num_sms; };
 
+struct CsParams {        // k_conv_stream.cu: streaming convolution, one 32-channel (or single-channel) output slice per unit
+  TV in, out, res;       // split-fp16 C8 tensors (out/res unused for plane output)
+  const __half* w; const float* bias;
+  float* out_plane; const float* res_plane;          // cout == 1: fp32 [n][D][H][W]
+  int N, D, H, W, dil, kz, nk16, in_pad;
+  int nco, ccs;          // output channels per unit (32, or 16 with one real channel), number of slices
+  int XW, strips, nchunk, rpc, total_units, nxs;
+  int relu, res_mode;    // res_mode 0: C8 tensor like out (or none), 1: channel 0 of a C8 tensor, 2: fp32 plane
+  uint32_t sub_bytes, slot_bytes, w_bytes;
+};
+struct CsPlan { CsParams p; size_t smem; int num_sms; };
+
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 // Programmatic dependent launch: every kernel of the pass is launched with the stream-serialization attribute and

@@ -1,0 +1,418 @@
+// Streaming tcgen05 convolution (SNB_PREC_TC_F16X2): stride-1 3x3 / 3x3x3 convolutions with the weights of one
+// 32-output-channel slice RESIDENT in shared memory and the input streamed row by row - the single-convolution
+// sibling of k_resblock_tc.cu.  Covers SURVEY.md §8a rows M1 (layer2-4, firstconv.1), M3 (head.filter.1-4,
+// conv3d_alone) and M5 (refinement conv_out).
+//
+//   unit          (output-channel slice, sample, depth, 128-pixel strip, comb, row chunk); a CTA walks DOWN the rows
+//                 of its unit.  Per input row one "job": for every depth tap and every 16-channel chunk of the input,
+//                 9 MMAs (3 kernel columns x {hi*hi, hi*lo, lo*hi}) accumulate into ONE TMEM slot of 3*NCO columns:
+//                 M = 128 pixels, N = NCO output channels x 3 kernel rows, K = 16.  Row i of the input therefore
+//                 contributes to output rows i-1, i, i+1; the epilogue keeps two partial output rows in registers.
+//   NCO           32: C8 split-fp16 output (+ bias, optional residual, optional ReLU).
+//                 16: single-output-channel convolutions (channel 0 real, 1-15 zero weights: N must be a multiple
+//                     of 16 at M = 128) writing an fp32 plane (+ bias, optional residual, optional ReLU).
+//   pipeline      warp 0 bulk-copy producer (weights when the channel slice changes, then one ring entry per
+//                 (row, depth tap, 16-channel chunk)), warp 1 TMEM owner + MMA issuer, warps 2-5 epilogue.
+//                 5 TMEM slots decouple the issuer from the epilogue; no end-of-tile burst: every drained job emits
+//                 one finished output row.
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "tc_ptx.cuh"
+
+namespace snb {
+
+using namespace ptx;
+
+constexpr int CS_THREADS = 192;
+constexpr int CS_EPI_WARPS = 4;
+constexpr int CS_SLOTS = 5;
+
+struct CsUnit { int cc, n, d, x0, c, i0, nr; };
+
+__device__ __forceinline__ CsUnit cs_decode(const CsParams& p, int u) {
+  CsUnit r;
+  const int chunk = u % p.nchunk; u /= p.nchunk;
+  r.c = u % p.dil; u /= p.dil;
+  const int strip = u % p.strips; u /= p.strips;
+  r.d = u % p.D; u /= p.D;
+  r.n = u % p.N;
+  r.cc = u / p.N;                               // slowest index: a CTA rarely changes its weight slice
+  r.x0 = strip * 128;
+  const int rc = r.c < p.H ? (p.H - r.c + p.dil - 1) / p.dil : 0;
+  r.i0 = chunk * p.rpc;
+  r.nr = min(rc, r.i0 + p.rpc) - r.i0;
+  return r;
+}
+
+__device__ __forceinline__ void cs_ld3x16(uint32_t c0, uint32_t c1, uint32_t c2, float (&v0)[16], float (&v1)[16], float (&v2)[16]) {
+  uint32_t r[48];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%48];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%49];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47}, [%50];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
+        "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+        "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47])
+      : "r"(c0), "r"(c1), "r"(c2) : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { v0[i] = __uint_as_float(r[i]); v1[i] = __uint_as_float(r[16 + i]); v2[i] = __uint_as_float(r[32 + i]); }
+}
+
+__device__ __forceinline__ void cs_split8(const float* f, uint4& oh, uint4& ol) {
+  __half2* ph = reinterpret_cast<__half2*>(&oh);
+  __half2* pl = reinterpret_cast<__half2*>(&ol);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __half2 hh = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+    const float2 hf = __half22float2(hh);
+    ph[j] = hh;
+    pl[j] = __floats2half2_rn(f[2 * j] - hf.x, f[2 * j + 1] - hf.y);
+  }
+}
+
+template <int NCO>
+__global__ void __launch_bounds__(CS_THREADS, 1) k_conv_stream(const CsParams p) {
+  constexpr int NCOL = 3 * NCO;                // accumulator columns of one job: [ky][NCO]
+  constexpr int SLOT_STRIDE = NCO == 32 ? 96 : 64;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ float s_bias[32];
+  __shared__ uint64_t bars[48];
+  __shared__ uint32_t tmem_slot;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  uint8_t* s_w = smem;                                     // [k16][dz][kx][chunk][2*NCOL rows][8 halfs]
+  uint8_t* s_x = smem + p.w_bytes;                         // ring of [plane][chunk][XW px][8 halfs]
+  uint64_t* w_full = bars;
+  uint64_t* w_empty = bars + 1;
+  uint64_t* x_full = bars + 2;
+  uint64_t* x_empty = x_full + p.nxs;                      // nxs <= 16
+  uint64_t* s_full = bars + 36;
+  uint64_t* s_empty = s_full + CS_SLOTS;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    mbar_init(w_full, 1); mbar_init(w_empty, 1);
+    for (int i = 0; i < p.nxs; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+    for (int i = 0; i < CS_SLOTS; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], CS_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_trigger();
+  pdl_wait();
+  const uint32_t tmem_base = tmem_slot;
+  const int d = p.dil, zpad = p.kz >> 1;
+  const uint32_t wblk = 3 * 2 * 2 * NCOL * 16;              // weight bytes of one (k16, dz): [kx][chunk][2*NCOL][8]
+
+  if (warp == 0) {
+    // ================================ bulk-copy producer ================================
+    const __half* in = static_cast<const __half*>(p.in.p);
+    uint32_t it = 0, nw = 0;
+    int cur_cc = -1;
+    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+      const CsUnit un = cs_decode(p, u);
+      if (un.nr <= 0) continue;
+      if (un.cc != cur_cc) {                                 // (re)load this slice's weights once every MMA reading the old ones retired
+        if (lane == 0) {
+          mbar_wait(w_empty, (nw & 1) ^ 1);
+          mbar_expect_tx(w_full, p.w_bytes);
+          bulk_load(s_w, p.w + (size_t)un.cc * (p.w_bytes / 2), p.w_bytes, w_full);
+        }
+        cur_cc = un.cc; ++nw;
+      }
+      for (int j = 0; j < un.nr + 2; ++j) {
+        const int row = min(un.c + d * (un.i0 - 1 + j), p.H + p.in_pad - 1);
+        for (int dz = 0; dz < p.kz; ++dz) {
+          const int zin = un.d + dz - zpad;
+          if (zin < 0 || zin >= p.D) continue;
+          for (int k16 = 0; k16 < p.nk16; ++k16, ++it) {
+            const uint32_t slot = it % p.nxs;
+            if (lane == 0) {
+              mbar_wait(&x_empty[slot], ((it / p.nxs) & 1) ^ 1);
+              mbar_expect_tx(&x_full[slot], 4 * p.sub_bytes);
+            }
+            __syncwarp();
+            if (lane < 4) {                                 // lane = plane*2 + chunk
+              const __half* src = in + (size_t)un.n * p.in.ss + (size_t)(lane >> 1) * p.in.lo +
+                                  ((size_t)(k16 * 2 + (lane & 1)) * p.D + zin) * p.in.slice +
+                                  ((ptrdiff_t)row * p.in.ws + (un.x0 - d)) * 8;
+              bulk_load(s_x + (size_t)slot * p.slot_bytes + (size_t)lane * p.sub_bytes, src, p.sub_bytes, &x_full[slot]);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_f16(128, NCOL);
+    const uint32_t b_lbo = 2 * NCOL * 16;                   // bytes between the two K halves of a weight block
+    const uint32_t dil16 = (uint32_t)d;
+    const uint32_t w_addr = smem_u32(s_w);
+    uint32_t it = 0, nj = 0, nw = 0;
+    int cur_cc = -1;
+    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+      const CsUnit un = cs_decode(p, u);
+      if (un.nr <= 0) continue;
+      if (un.cc != cur_cc) { mbar_wait(w_full, nw & 1); cur_cc = un.cc; ++nw; }
+      for (int j = 0; j < un.nr + 2; ++j, ++nj) {
+        const uint32_t ts = nj % CS_SLOTS;
+        mbar_wait(&s_empty[ts], ((nj / CS_SLOTS) & 1) ^ 1);
+        const uint32_t dcol = tmem_base + ts * SLOT_STRIDE;
+        bool first = true;
+        for (int dz = 0; dz < p.kz; ++dz) {
+          const int zin = un.d + dz - zpad;
+          if (zin < 0 || zin >= p.D) continue;
+          for (int k16 = 0; k16 < p.nk16; ++k16, ++it) {
+            const uint32_t slot = it % p.nxs;
+            mbar_wait(&x_full[slot], (it / p.nxs) & 1);
+            tc_fence_after();
+            if (leader) {
+              const uint32_t a_addr = smem_u32(s_x + (size_t)slot * p.slot_bytes);
+              const uint64_t a_hi = make_smem_desc(a_addr, p.sub_bytes, 128);
+              const uint64_t a_lo = make_smem_desc(a_addr + 2 * p.sub_bytes, p.sub_bytes, 128);
+              const uint32_t wb = w_addr + (uint32_t)(k16 * p.kz + dz) * wblk;
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                const uint64_t w_hi = make_smem_desc(wb + (uint32_t)(kx * 2) * b_lbo, b_lbo, 128);
+                const uint64_t w_lo = w_hi + (uint64_t)NCOL;            // + NCOL rows x 16 B
+                const uint64_t sh = (uint64_t)(kx * dil16);
+                if (first && kx == 0) umma_f16_zero(dcol, a_hi, w_hi, idesc);
+                else umma_f16_acc(dcol, a_hi + sh, w_hi, idesc);
+                umma_f16_acc(dcol, a_hi + sh, w_lo, idesc);
+                umma_f16_acc(dcol, a_lo + sh, w_hi, idesc);
+              }
+              umma_commit(&x_empty[slot]);
+            }
+            __syncwarp();
+            first = false;
+          }
+        }
+        if (leader) umma_commit(&s_full[ts]);
+        __syncwarp();
+      }
+      // the next unit of this CTA needs other weights: tell the producer when the MMAs above have retired
+      int un_next = u + gridDim.x;
+      while (un_next < p.total_units && cs_decode(p, un_next).nr <= 0) un_next += gridDim.x;
+      if (un_next < p.total_units && cs_decode(p, un_next).cc != cur_cc) {
+        if (leader) umma_commit(w_empty);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================================ epilogue ================================
+    const int m = (warp & 3) * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t nj = 0;
+    int cur_cc = -1;
+    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+      const CsUnit un = cs_decode(p, u);
+      if (un.nr <= 0) continue;
+      if (un.cc != cur_cc) {
+        // all four epilogue warps use the same 32 biases; a named barrier keeps the refill ordered within the group
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x - 64 < 32) s_bias[threadIdx.x - 64] = (NCO == 32 || threadIdx.x == 64) ? p.bias[un.cc * NCO + (threadIdx.x - 64)] : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        cur_cc = un.cc;
+      }
+      const int opx = un.x0 + m;
+      const bool col_ok = opx < p.W;
+      if constexpr (NCO == 32) {
+        const __half* res = static_cast<const __half*>(p.res.p);
+        __half* out = static_cast<__half*>(p.out.p);
+        float a0[32], a1[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) a0[c] = a1[c] = 0.f;
+        const size_t o_base = (size_t)un.n * p.out.ss + ((size_t)(un.cc * 4) * p.D + un.d) * p.out.slice + (size_t)opx * 8;
+        const size_t r_base = (size_t)un.n * p.res.ss + ((size_t)(un.cc * 4) * p.D + un.d) * p.res.slice + (size_t)opx * 8;
+        for (int j = 0; j < un.nr + 2; ++j, ++nj) {
+          const uint32_t ts = nj % CS_SLOTS;
+          const int row = un.c + d * (un.i0 - 2 + j);       // the output row this job completes
+          const bool ok = col_ok && j >= 2 && row < p.H;
+          uint4 rh[4], rl[4];
+          if (ok && res) {                                  // residual prefetch while the job's MMAs finish
+            const __half* rp = res + r_base + (size_t)row * p.res.ws * 8;
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) {
+              rh[cb] = __ldg(reinterpret_cast<const uint4*>(rp + (size_t)cb * p.D * p.res.slice));
+              rl[cb] = __ldg(reinterpret_cast<const uint4*>(rp + (size_t)cb * p.D * p.res.slice + p.res.lo));
+            }
+          }
+          mbar_wait(&s_full[ts], (nj / CS_SLOTS) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            float v0[16], v1[16], v2[16];
+            const uint32_t col = lane_addr + ts * SLOT_STRIDE + hf * 16;
+            cs_ld3x16(col, col + 32, col + 64, v0, v1, v2);
+            if (hf == 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&s_empty[ts]);
+            }
+            if (ok) {
+              __half* op = out + o_base + (size_t)row * p.out.ws * 8;
+#pragma unroll
+              for (int jb = 0; jb < 2; ++jb) {
+                const int cb = hf * 2 + jb;
+                float f[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) f[q] = a0[hf * 16 + jb * 8 + q] + v2[jb * 8 + q];
+                if (res) {
+                  const __half2* h2 = reinterpret_cast<const __half2*>(&rh[cb]);
+                  const __half2* l2 = reinterpret_cast<const __half2*>(&rl[cb]);
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const float2 a = __half22float2(h2[q]), b = __half22float2(l2[q]);
+                    f[2 * q] += a.x + b.x; f[2 * q + 1] += a.y + b.y;
+                  }
+                }
+                if (p.relu) {
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) f[q] = fmaxf(f[q], 0.f);
+                }
+                uint4 oh, ol;
+                cs_split8(f, oh, ol);
+                *reinterpret_cast<uint4*>(op + (size_t)cb * p.D * p.out.slice) = oh;
+                *reinterpret_cast<uint4*>(op + (size_t)cb * p.D * p.out.slice + p.out.lo) = ol;
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < 16; ++c) { a0[hf * 16 + c] = a1[hf * 16 + c] + v1[c]; a1[hf * 16 + c] = v0[c] + s_bias[hf * 16 + c]; }
+          }
+        }
+      } else {
+        // single output channel: columns [ky*16 + 0]; fp32 plane out [n][D][H][W], optional residual
+        float a0 = 0.f, a1 = 0.f;
+        const float bias = s_bias[0];
+        for (int j = 0; j < un.nr + 2; ++j, ++nj) {
+          const uint32_t ts = nj % CS_SLOTS;
+          const int row = un.c + d * (un.i0 - 2 + j);
+          const bool ok = col_ok && j >= 2 && row < p.H;
+          float r = 0.f;
+          const size_t o = (((size_t)un.n * p.D + un.d) * p.H + (ok ? row : 0)) * p.W + (ok ? opx : 0);
+          if (ok && p.res_mode == 1) {                      // channel 0 of a C8 split-fp16 tensor
+            const __half* rp = static_cast<const __half*>(p.res.p) + (size_t)un.n * p.res.ss + ((size_t)row * p.res.ws + opx) * 8;
+            r = __half2float(__ldg(rp)) + __half2float(__ldg(rp + p.res.lo));
+          } else if (ok && p.res_mode == 2) {
+            r = __ldg(p.res_plane + o);
+          }
+          mbar_wait(&s_full[ts], (nj / CS_SLOTS) & 1);
+          tc_fence_after();
+          float v0[16], v1[16], v2[16];
+          const uint32_t col = lane_addr + ts * SLOT_STRIDE;
+          cs_ld3x16(col, col + 16, col + 32, v0, v1, v2);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[ts]);
+          if (ok) {
+            float f = a0 + v2[0] + r;
+            if (p.relu) f = fmaxf(f, 0.f);
+            p.out_plane[o] = f;
+          }
+          a0 = a1 + v1[0];
+          a1 = v0[0] + bias;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+// Weight packing: [cc][k16][dz][kx][K half][2*3*NCO rows][8]: rows [W_hi: ky*NCO + co | W_lo: 3*NCO + ky*NCO + co]
+void cs_pack_weights(const float* W, int cout, int cin, int kz, int NCO, std::vector<__half>& out) {
+  const int ccs = NCO == 32 ? cout / 32 : 1, nk16 = cin / 16, ncol = 3 * NCO;
+  out.assign((size_t)ccs * nk16 * kz * 3 * 2 * 2 * ncol * 8, __float2half(0.f));
+  for (int co = 0; co < cout; ++co)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int dz = 0; dz < kz; ++dz)
+        for (int ky = 0; ky < 3; ++ky)
+          for (int kx = 0; kx < 3; ++kx) {
+            const float v = W[((((size_t)co * cin + ci) * kz + dz) * 3 + ky) * 3 + kx];
+            const __half hi = __float2half_rn(v);
+            const __half lo = __float2half_rn(v - __half2float(hi));
+            const int cc = NCO == 32 ? co / 32 : 0, cl = NCO == 32 ? co % 32 : co;
+            const int k16 = ci / 16, half = (ci % 16) / 8, e = ci % 8;
+            const size_t blk = ((((size_t)cc * nk16 + k16) * kz + dz) * 3 + kx) * 2 + half;
+            out[(blk * 2 * ncol + ky * NCO + cl) * 8 + e] = hi;
+            out[(blk * 2 * ncol + ncol + ky * NCO + cl) * 8 + e] = lo;
+          }
+}
+
+// in: split-fp16 C8 tensor with pad >= dil, cin % 16 == 0.  cout % 32 == 0 (C8 output) or cout == 1 (plane output).
+cudaError_t conv_stream_plan(CsPlan* plan, const Tens& in, int cin, int cout, int dil, int kz, int num_sms) {
+  if (cin % 16 || !(cout % 32 == 0 || cout == 1) || in.planes != 2 || in.pad < dil || dil < 1 || dil > 16 || (kz != 1 && kz != 3))
+    return cudaErrorInvalidValue;
+  *plan = CsPlan();
+  CsParams& p = plan->p;
+  p.in = view(in);
+  p.D = in.d; p.H = in.h; p.W = in.w; p.dil = dil; p.kz = kz; p.nk16 = cin / 16; p.in_pad = in.pad;
+  p.nco = cout == 1 ? 16 : 32;
+  p.ccs = cout == 1 ? 1 : cout / 32;
+  p.XW = 128 + 2 * dil;
+  p.sub_bytes = (uint32_t)p.XW * 16;
+  p.slot_bytes = 4 * p.sub_bytes;
+  p.strips = cdiv(p.W, 128);
+  p.w_bytes = (uint32_t)(p.nk16 * kz) * (3 * 2 * 2 * 3 * p.nco * 16);
+  plan->num_sms = num_sms;
+  const long avail = 227L * 1024 - 2048 - 128 - (long)p.w_bytes;
+  int nxs = avail > 0 ? (int)(avail / p.slot_bytes) : 0;
+  nxs = nxs > 16 ? 16 : nxs;
+  // the ring must hold more than one job's entries or the producer cannot run ahead of the issuer
+  if (nxs < 4 || nxs < p.nk16 + 1) return cudaErrorInvalidValue;
+  p.nxs = nxs;
+  plan->smem = 128 + (size_t)p.w_bytes + (size_t)nxs * p.slot_bytes;
+  return cudaSuccess;
+}
+
+template <int NCO>
+static cudaError_t cs_launch_t(const CsParams& p, int grid, size_t smem, cudaStream_t st) {
+  static bool attr_done[32] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 31]) {
+    cudaFuncSetAttribute(k_conv_stream<NCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    attr_done[dev & 31] = true;
+  }
+  return launch_k(k_conv_stream<NCO>, grid, CS_THREADS, smem, st, p);
+}
+
+cudaError_t launch_conv_stream(const CsPlan& plan, int N, const void* w, const float* bias, const Tens* out, const Tens* res,
+                               float* out_plane, const float* res_plane, int res_c8_ch0, int relu, cudaStream_t st) {
+  CsParams p = plan.p;
+  p.N = N; p.w = static_cast<const __half*>(w); p.bias = bias; p.relu = relu;
+  if (out) p.out = view(*out);
+  p.res_mode = 0;
+  if (res) { p.res = view(*res); p.res_mode = res_c8_ch0 ? 1 : 0; }
+  if (res_plane) { p.res_plane = res_plane; p.res_mode = 2; }
+  p.out_plane = out_plane;
+  const int rc_max = cdiv(p.H, p.dil);
+  const long columns = (long)p.ccs * N * p.D * p.strips * p.dil;
+  int nchunk = (int)(plan.num_sms / columns);
+  if (nchunk < 1) nchunk = 1;
+  if (nchunk > cdiv(rc_max, 2)) nchunk = cdiv(rc_max, 2);
+  p.rpc = cdiv(rc_max, nchunk);
+  p.nchunk = cdiv(rc_max, p.rpc);
+  p.total_units = (int)(columns * p.nchunk);
+  const int grid = p.total_units < plan.num_sms ? p.total_units : plan.num_sms;
+  cudaError_t e = p.nco == 32 ? cs_launch_t<32>(p, grid, plan.smem, st) : cs_launch_t<16>(p, grid, plan.smem, st);
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+}  // namespace snb

@@ -185,6 +185,28 @@ struct Builder {
     return cw.w_tc[NT];
   }
 
+  // device copy of the k_conv_stream packing (NCO = 32: C8 output slices, 16: single output channel)
+  const __half* stream_weights(const std::string& name, ConvW& cw, int nco) {
+    const int key = 100 + nco;
+    if (!cw.w_tc.count(key)) {
+      std::vector<__half> packed;
+      cs_pack_weights(c->wts[name + ".weight"].data.data(), cw.cout, cw.cin, cw.kz, nco, packed);
+      __half* dw = nullptr;
+      if (cudaMalloc(&dw, packed.size() * sizeof(__half)) != cudaSuccess) { fail = true; return nullptr; }
+      cudaMemcpy(dw, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice);
+      c->wallocs.push_back(dw);
+      cw.w_tc[key] = dw;
+    }
+    return cw.w_tc[key];
+  }
+  bool stream_ok(const ConvW& cw, const Tens& in, int stride, int dil, CsPlan* plan) const {
+    if (c->planes != 2 || (c->cfg.flags & (SNB_FLAG_NO_TENSOR | SNB_FLAG_NO_STREAM)) || stride != 1 || cw.ks != 3) return false;
+    if (conv_stream_plan(plan, in, cw.cin, cw.cout, dil, cw.kz, c->num_sms) != cudaSuccess) return false;
+    // measured on config 2 (profiles/): resident weights pay off while one slice stays under ~80 KB (firstconv.1 29 vs 39 us,
+    // layer2 equal, conv_out 41 vs 52, conv3d_alone 44 vs 64); above that the staged k_conv_tc tiles win (layer3/4 28 vs 32 us)
+    return cw.cout == 1 || plan->p.w_bytes <= 80 * 1024;
+  }
+
   // out = ReLU(conv_b(ReLU(conv_a(in))) + res) with 32 channels, as ONE launch when the tcgen05 path allows it
   bool block_fusable(const std::string& prefix, const Tens& in, int dil) const {
     auto ia = c->convs.find(prefix + ".conv_a"), ib = c->convs.find(prefix + ".conv_b");
@@ -223,6 +245,22 @@ struct Builder {
     const double px = (double)nmul * in.d * ho * wo;
     op.flops = 2.0 * px * cw.cout * cw.cin * cw.ks * cw.ks * cw.kz;
     op.bytes = 4.0 * (nmul * (double)in.d * in.h * in.w * in.cb * 8 + px * out.cb * 8 * (res ? 2 : 1));
+    CsPlan splan;
+    if (stream_ok(cw, in, stride, dil, &splan)) {
+      const __half* dw = stream_weights(name, cw, 32);
+      if (!dw) return out;
+      const float* bias = cw.b;
+      const bool has_res = res != nullptr;
+      const Tens rt = res ? *res : Tens();
+      const int rl = relu ? 1 : 0;
+      op.fn = [splan, nmul, dw, bias, out, has_res, rt, rl](int B, cudaStream_t st) {
+        return launch_conv_stream(splan, nmul * B, dw, bias, &out, has_res ? &rt : nullptr, nullptr, nullptr, 0, rl, st);
+      };
+      op.name += " [tc-stream]";
+      ++c->n_tc_convs;
+      c->ops.push_back(op);
+      return out;
+    }
     if (tc_eligible(cw, stride) && in.pad >= dil) {
       TcConvPlan plan;
       cudaError_t e = tc_conv_plan(&plan, in, out, cw.cin, cw.cout, dil, cw.kz, c->num_sms);
@@ -258,8 +296,28 @@ struct Builder {
   Plane conv_to1(const std::string& name, const Tens& in, int dil, bool relu, const Tens* res_c8) {
     auto it = c->convs.find(name);
     if (it == c->convs.end()) { fail = true; snprintf(c->err, sizeof(c->err), "no weights for %s", name.c_str()); return Plane(); }
-    const ConvW cw = it->second;
+    ConvW& cw = it->second;
     Plane out = palloc(in.d, in.h, in.w);
+    CsPlan splan;
+    if (cw.cin % 16 == 0 && stream_ok(cw, in, 1, dil, &splan)) {
+      const __half* dw = stream_weights(name, cw, 16);
+      if (!dw) return out;
+      const float* bias = cw.b;
+      const bool has_res = res_c8 != nullptr;
+      const Tens rt = res_c8 ? *res_c8 : Tens();
+      const int rl = relu ? 1 : 0;
+      float* op_ = out.p;
+      Op op; op.name = name + " [tc-stream]";
+      op.fn = [splan, dw, bias, op_, has_res, rt, rl](int B, cudaStream_t st) {
+        return launch_conv_stream(splan, B, dw, bias, nullptr, has_res ? &rt : nullptr, op_, nullptr, 1, rl, st);
+      };
+      const double px = (double)in.d * in.h * in.w;
+      op.flops = 2.0 * px * cw.cin * 9 * cw.kz;
+      op.bytes = 4.0 * (px * in.cb * 8 + px * (res_c8 ? 2 : 1));
+      ++c->n_tc_convs;
+      c->ops.push_back(op);
+      return out;
+    }
     ConvTo1Params p{};
     p.in = view(in); p.out = out.p; p.w = cw.w; p.bias = cw.b0;
     p.res_c8 = res_c8 ? 1 : 0;
