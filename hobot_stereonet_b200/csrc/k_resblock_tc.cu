@@ -8,9 +8,12 @@
 //                 so vertical taps stay inside the comb).  Per row it runs two "jobs" on the tensor core:
 //                   a-job(i): x row i  (smem ring, bulk-copied)  x  Wa  -> contribution to y rows i-1, i, i+1
 //                   b-job(i): y row i  (smem ring, written by epilogue group A) x Wb -> out rows i-1, i, i+1
-//                 GEMM view: M = 128 pixels of the input row, N = 32 channels x 3 kernel rows = 96, K = 16
-//                 channels per MMA; the kernel column is a 16-byte shift of the A descriptor.  A job is 18 MMAs
-//                 (2 channel chunks x 3 columns x {hi*hi, hi*lo, lo*hi}) chained in ONE 96-column TMEM slot.
+//                 GEMM view: M = 128 pixels of the input row, K = 16 channels per MMA, N = 32 channels x 3 kernel rows
+//                 stacked with the hi/lo weight halves: A_hi x [W_hi | W_lo] (N = 192 -> main | corr columns) and
+//                 A_lo x W_hi (N = 96 -> corr); the kernel column is a 16-byte shift of the A descriptor.  A job is
+//                 12 MMAs (2 channel chunks x 3 columns x 2) chained in one 192-column TMEM slot.  (Three N = 96
+//                 MMAs into one 96-column accumulator were measured 25 % slower: each re-reads the 4 KB A tile and
+//                 the job becomes shared-memory-bandwidth-bound.)
 //   halo          only 4 extra rows at the top of a column walk (two per conv) instead of 2 per 6-row tile twice.
 //   epilogue      two warp groups, one per conv, so the y emission and the output emission overlap:
 //                 group A (warps 2-5) drains a-jobs, keeps two partial y rows in fp32 registers; a finished row gets
@@ -18,7 +21,8 @@
 //                 in the A-operand layout.  Group B (warps 6-9) drains b-jobs; a finished output row gets the
 //                 residual, ReLU, the split, and goes to HBM.  Biases are added when a partial row is born.
 //   pipeline      warp 0: bulk-copy producer (weights once, then one x row per a-job), warp 1: TMEM owner + MMA
-//                 issuer.  TMEM: 3 slots for a-jobs + 2 for b-jobs (5 x 96 columns), full/empty mbarriers each.
+//                 issuer.  TMEM: one 192-column slot per conv; a-jobs and b-jobs alternate on the tensor pipe, so
+//                 the drain of an a-job overlaps the MMAs of the following b-job and vice versa.
 //                 Persistent over (sample, strip, comb, row-chunk) units.
 #include <stdlib.h>
 
@@ -34,10 +38,10 @@ using namespace ptx;
 
 constexpr int RB_THREADS = 320;
 constexpr int RB_GROUP_WARPS = 4;
-constexpr int RB_SLOT_COLS = 96;                        // [half][ky][16 ch]
+constexpr int RB_SLOT_COLS = 192;                       // [main | corr] x [half][ky][16 ch]
 constexpr int RB_WROWS = 192;                           // packed weight rows per (k16, kx, chunk): [W_hi 96 | W_lo 96]
 constexpr uint32_t RB_W_BYTES = 2 * 3 * 2 * RB_WROWS * 16;   // one conv: [k16][kx][chunk][192 rows][8 halfs]
-constexpr int RB_YSLOTS = 3, RB_ASLOTS = 3, RB_BSLOTS = 2;
+constexpr int RB_YSLOTS = 3, RB_ASLOTS = 1, RB_BSLOTS = 1;
 
 struct RbUnit { int n, x0, c, i0, nr; };
 
@@ -55,26 +59,12 @@ __device__ __forceinline__ RbUnit rb_decode(const RbParams& p, int u) {
   return r;
 }
 
-// Three 32-lane x 16-column fp32 loads (kernel rows 0..2 of one 16-channel half) and the wait in one asm statement.
-__device__ __forceinline__ void rb_drain(uint32_t col, float (&v0)[16], float (&v1)[16], float (&v2)[16]) {
-  uint32_t r[48];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%48];\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%49];\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47}, [%50];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
-        "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
-        "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47])
-      : "r"(col), "r"(col + 16), "r"(col + 32) : "memory");
+// one kernel row of one 16-channel half: main + corr columns
+__device__ __forceinline__ void rb_ld_sum(uint32_t col, float (&v)[16]) {
+  float m[16], c[16];
+  tmem_ld_2x16(col, col + RB_SLOT_COLS / 2, m, c);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) { v0[i] = __uint_as_float(r[i]); v1[i] = __uint_as_float(r[16 + i]); v2[i] = __uint_as_float(r[32 + i]); }
+  for (int i = 0; i < 16; ++i) v[i] = m[i] + c[i];
 }
 
 __device__ __forceinline__ void rb_split8(const float* f, uint4& oh, uint4& ol) {
@@ -171,14 +161,14 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     const bool leader = elect_one();
-    const uint32_t idesc = make_idesc_f16(128, RB_SLOT_COLS);
+    const uint32_t idesc1 = make_idesc_f16(128, RB_SLOT_COLS), idesc2 = make_idesc_f16(128, RB_SLOT_COLS / 2);
     const uint32_t b_lbo = RB_WROWS * 16;
     const uint32_t dil16 = (uint32_t)d;                     // descriptor address units of 16 B = one pixel
     const uint32_t wa_addr = smem_u32(s_wa), wb_addr = smem_u32(s_wb);
     mbar_wait(w_full, 0);
     uint32_t na = 0, nb = 0, itx = 0;
 
-    // 18 MMAs of one job: A rows from `a_addr` ([plane][chunk][px][8]), weights from `w_addr`, one accumulator
+    // 12 MMAs of one job: A rows from `a_addr` ([plane][chunk][px][8]), weights from `w_addr`
     auto issue_job = [&](uint32_t a_addr, uint32_t w_addr, uint32_t dcol) {
 #pragma unroll
       for (int k16 = 0; k16 < 2; ++k16) {
@@ -186,13 +176,11 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
         const uint64_t a_lo = make_smem_desc(a_addr + (uint32_t)(4 + 2 * k16) * p.sub_bytes, p.sub_bytes, 128);
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const uint64_t w_hi = make_smem_desc(w_addr + (uint32_t)((k16 * 3 + kx) * 2) * b_lbo, b_lbo, 128);
-          const uint64_t w_lo = w_hi + (uint64_t)RB_SLOT_COLS;        // +96 rows x 16 B, in 16-byte units
+          const uint64_t db = make_smem_desc(w_addr + (uint32_t)((k16 * 3 + kx) * 2) * b_lbo, b_lbo, 128);
           const uint64_t sh = (uint64_t)(kx * dil16);
-          if (k16 == 0 && kx == 0) umma_f16_zero(dcol, a_hi, w_hi, idesc);
-          else umma_f16_acc(dcol, a_hi + sh, w_hi, idesc);
-          umma_f16_acc(dcol, a_hi + sh, w_lo, idesc);
-          umma_f16_acc(dcol, a_lo + sh, w_hi, idesc);
+          if (k16 == 0 && kx == 0) umma_f16_zero(dcol, a_hi, db, idesc1);
+          else umma_f16_acc(dcol, a_hi + sh, db, idesc1);
+          umma_f16_acc(dcol + RB_SLOT_COLS / 2, a_lo + sh, db, idesc2);
         }
       }
     };
@@ -258,19 +246,15 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
         const long long c0 = PROF ? clock64() : 0;
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
-          float v0[16], v1[16], v2[16];
-          rb_drain(lane_addr + ts * RB_SLOT_COLS + hf * 48, v0, v1, v2);
-          if (hf == 1) {                       // the slot is in registers: hand it back to the issuer
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sa_empty[ts]);
-          }
+          const uint32_t col = lane_addr + ts * RB_SLOT_COLS + hf * 48;
+          float v[16];
+          rb_ld_sum(col + 32, v);              // kernel row 2 completes the oldest partial row
           if (ja >= 2) {
 #pragma unroll
             for (int jb = 0; jb < 2; ++jb) {
               float f[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = ok ? fmaxf(a0[hf * 16 + jb * 8 + j] + v2[jb * 8 + j], 0.f) : 0.f;
+              for (int j = 0; j < 8; ++j) f[j] = ok ? fmaxf(a0[hf * 16 + jb * 8 + j] + v[jb * 8 + j], 0.f) : 0.f;
               uint4 oh, ol;
               rb_split8(f, oh, ol);
               const uint32_t a = sy_addr + ys * p.slot_bytes + (uint32_t)(hf * 2 + jb) * p.sub_bytes;
@@ -278,8 +262,17 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
               rb_sts16(a + 4 * p.sub_bytes, ol);
             }
           }
+          rb_ld_sum(col + 16, v);
 #pragma unroll
-          for (int c = 0; c < 16; ++c) { a0[hf * 16 + c] = a1[hf * 16 + c] + v1[c]; a1[hf * 16 + c] = v0[c] + s_bias[hf * 16 + c]; }
+          for (int c = 0; c < 16; ++c) a0[hf * 16 + c] = a1[hf * 16 + c] + v[c];
+          rb_ld_sum(col, v);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) a1[hf * 16 + c] = v[c] + s_bias[hf * 16 + c];
+          if (hf == 1) {                       // the slot is in registers: hand it back to the issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sa_empty[ts]);
+          }
         }
         if (ja >= 2) {
           fence_proxy_async();
@@ -331,13 +324,9 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
         const long long c0 = PROF ? clock64() : 0;
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
-          float v0[16], v1[16], v2[16];
-          rb_drain(lane_addr + ts * RB_SLOT_COLS + hf * 48, v0, v1, v2);
-          if (hf == 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sb_empty[ts]);
-          }
+          const uint32_t col = lane_addr + ts * RB_SLOT_COLS + hf * 48;
+          float v[16];
+          rb_ld_sum(col + 32, v);
           if (ok) {
             __half* op = out + o_base + (size_t)row * p.out.ws * 8;
 #pragma unroll
@@ -350,8 +339,8 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
               for (int j = 0; j < 4; ++j) {
                 const float2 a = __half22float2(h2[j]), b = __half22float2(l2[j]);
                 const int c = jb * 8 + 2 * j;
-                f[2 * j] = fmaxf(b0[hf * 16 + c] + v2[c] + (a.x + b.x), 0.f);
-                f[2 * j + 1] = fmaxf(b0[hf * 16 + c + 1] + v2[c + 1] + (a.y + b.y), 0.f);
+                f[2 * j] = fmaxf(b0[hf * 16 + c] + v[c] + (a.x + b.x), 0.f);
+                f[2 * j + 1] = fmaxf(b0[hf * 16 + c + 1] + v[c + 1] + (a.y + b.y), 0.f);
               }
               uint4 oh, ol;
               rb_split8(f, oh, ol);
@@ -359,8 +348,17 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
               *reinterpret_cast<uint4*>(op + (size_t)cb * p.out.slice + p.out.lo) = ol;
             }
           }
+          rb_ld_sum(col + 16, v);
 #pragma unroll
-          for (int c = 0; c < 16; ++c) { b0[hf * 16 + c] = b1[hf * 16 + c] + v1[c]; b1[hf * 16 + c] = v0[c] + s_bias[32 + hf * 16 + c]; }
+          for (int c = 0; c < 16; ++c) b0[hf * 16 + c] = b1[hf * 16 + c] + v[c];
+          rb_ld_sum(col, v);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) b1[hf * 16 + c] = v[c] + s_bias[32 + hf * 16 + c];
+          if (hf == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sb_empty[ts]);
+          }
         }
         if (PROF) t_emit += clock64() - c0;
       }
