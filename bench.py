@@ -28,6 +28,9 @@ WORKLOAD = "SceneFlow-shape 540x960, 1/8-res cost volume D=24, 3x refinement, ba
 METRIC = "stereo pairs/sec at 540x960 D=24"
 SEED = 1234
 L2_BYTES = 126 * 1024 * 1024
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+# `ncu --set full` capture (profiles/): filled in by hand after each capture, None when not captured.
+TRAFFIC = {}
 
 
 def synth_inputs(n: int) -> np.ndarray:
@@ -209,23 +212,32 @@ def main():
         torch.cuda.synchronize(dev)
         ms = ev0.elapsed_time(ev1)
         barrier()
-        # ---- e2e: the reference-facing call with host buffers (sync DnnNode::Run semantics) ----
+        # ---- e2e: the reference-facing call with HOST buffers.  The node calls DnnNode::Run(is_sync=false) with
+        # task_num = 4 calls in flight (stereonet_node.cpp:144,812): snb_infer_async, pinned buffers, copies timed.
         for i in range(3):
             m.infer(host_in[i:i + 1].numpy(), host_out[i:i + 1].numpy())
         barrier()
         t0 = time.perf_counter()
         for i in range(args.steps):
             j = (3 + i) % pool_n
-            m.infer(host_in[j:j + 1].numpy(), host_out[j:j + 1].numpy())
+            m.infer_async(host_in[j:j + 1].numpy(), host_out[j:j + 1].numpy())
+        m.wait_all()
         torch.cuda.synchronize(dev)
         e2e_s = time.perf_counter() - t0
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):                      # same through the synchronous call, one pair in flight
+            j = (3 + i) % pool_n
+            m.infer(host_in[j:j + 1].numpy(), host_out[j:j + 1].numpy())
+        torch.cuda.synchronize(dev)
+        e2e_sync_s = time.perf_counter() - t0
     clocks = clk.summary()
     launches_per_step = m.rt_stat().kernel_launches
 
-    t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms, e2e_s * 1e3, e2e_sync_s * 1e3], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(t[0]), float(t[1])
+    ms, e2e_ms, e2e_sync_ms = float(t[0]), float(t[1]), float(t[2])
 
     result = None
     if rank == 0:
@@ -244,15 +256,27 @@ def main():
         tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)       # kernel timed inside a long step
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-        conv = [(n, v) for n, v in prof.items() if v[1] > 0 and n != "costvol"]
-        conv_ms = sum(v[0] for _, v in conv)
-        conv_fl = sum(v[1] for _, v in conv)
+        fam_of = lambda n: ("k_resblock_tc" if "[tc-block]" in n else "k_conv_stream" if "[tc-stream]" in n else
+                            "k_conv_tc" if "[tc]" in n else "k_costvol" if n == "costvol" else "cuda_core_and_hbm")
+        fam = {}
+        for n, v in prof.items():
+            a = fam.setdefault(fam_of(n), [0.0, 0.0, 0.0, 0])
+            a[0] += v[0]; a[1] += v[1]; a[2] += v[2]; a[3] += 1
         total_ms = sum(v[0] for v in prof.values())
-        cv = prof.get("costvol", [1e-9, 0, 0])
-        roofline = {"kernel": "k_conv_tc (tcgen05 implicit-GEMM conv)" if args.precision == "tc" else "k_conv_direct (fp32 CUDA-core conv)",
-                    "bound": "tensor", "achieved": conv_fl / (conv_ms * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
-                    "frac": conv_fl / (conv_ms * 1e-3) / 1e12 / tf_peak, "traffic": None, "peak_source": peak_src,
-                    "launches": len(conv), "share_of_step": conv_ms / total_ms,
+        tc_fams = {k: v for k, v in fam.items() if k in ("k_resblock_tc", "k_conv_stream", "k_conv_tc") or args.precision != "tc"}
+        dom = max(tc_fams, key=lambda k: tc_fams[k][0])
+        d = fam[dom]
+        cv = fam.get("k_costvol", [1e-9, 0, 0, 0])
+        tf = lambda v: v[1] / (v[0] * 1e-3) / 1e12
+        roofline = {"kernel": dom + (" (fused residual block: conv+ReLU+conv+residual+ReLU, tcgen05, split-fp16 operands = 3 fp16 MMAs per algorithmic MAC)"
+                                     if dom == "k_resblock_tc" else ""),
+                    "bound": "tensor", "achieved": tf(d), "peak": tf_peak, "unit": "TFLOP/s", "frac": tf(d) / tf_peak,
+                    "traffic": TRAFFIC.get(dom), "peak_source": peak_src, "launches": d[3], "share_of_step": d[0] / total_ms,
+                    "algorithmic_flops_per_launch": d[1] / max(d[3], 1), "avg_launch_ms": d[0] / max(d[3], 1),
+                    "families": {k: {"ms": v[0], "share": v[0] / total_ms, "launches": v[3],
+                                     "tflops": tf(v) if v[1] else None, "gbs": v[2] / (v[0] * 1e-3) / 1e9} for k, v in fam.items()},
+                    "all_tensor_kernels": {"achieved": sum(v[1] for v in tc_fams.values()) / (sum(v[0] for v in tc_fams.values()) * 1e-3) / 1e12,
+                                           "unit": "TFLOP/s"},
                     "hbm_kernels": {"costvol": {"bound": "hbm", "achieved": cv[2] / (cv[0] * 1e-3) / 1e9, "peak": hbm_peak,
                                                 "unit": "GB/s", "frac": cv[2] / (cv[0] * 1e-3) / 1e9 / hbm_peak}}}
         result = {
@@ -264,8 +288,10 @@ def main():
                        "l2": f"inputs rotate through a pool of {pool_n} tensors = {pool_n * in_bytes / 2**20:.0f} MiB > 126 MiB L2",
                        "parallelism": f"replicas x{world}, batch-sharded, one NCCL weight broadcast at init"},
             "e2e": {"value": world * args.steps * BATCH / (e2e_ms * 1e-3), "unit": "pairs/s",
-                    "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4 * H * W * BATCH, "api": "snb_infer (sync, pinned host buffers)"},
-            "gpu_launches": launches_per_step * args.steps * 2,      # device-resident loop + e2e loop
+                    "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4 * H * W * BATCH,
+                    "api": "snb_infer_async (4 calls in flight as the reference node, pinned host buffers)",
+                    "sync_value": world * args.steps * BATCH / (e2e_sync_ms * 1e-3), "sync_api": "snb_infer (one call in flight)"},
+            "gpu_launches": launches_per_step * args.steps * 3,      # device-resident loop + two e2e loops
             "clocks": clocks, "roofline": roofline,
         }
         if not args.no_cpu_baseline and world == 1:

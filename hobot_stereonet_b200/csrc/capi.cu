@@ -45,8 +45,8 @@ const char* snb_last_error(const snb_ctx* ctx) { return ctx ? ctx->err : g_err; 
 int snb_create(snb_ctx** out, const snb_config* cfg) {
   if (!out || !cfg || cfg->struct_size != (int32_t)sizeof(snb_config)) return fail(nullptr, SNB_ERR_INVALID, "snb_create: bad config struct");
   *out = nullptr;
-  if (cfg->height <= 0 || cfg->width <= 0 || (cfg->height & 1) || (cfg->width & 1))
-    return fail(nullptr, SNB_ERR_INVALID, "snb_create: height and width must be positive and even (NV12)");
+  if (cfg->height <= 0 || cfg->width <= 0)
+    return fail(nullptr, SNB_ERR_INVALID, "snb_create: height and width must be positive");
   if (cfg->K < 1 || cfg->K > 5 || cfg->D < 1 || cfg->D > 512 || cfg->max_batch < 1)
     return fail(nullptr, SNB_ERR_INVALID, "snb_create: need 1<=K<=5, 1<=D<=512, max_batch>=1");
   if (cfg->precision != SNB_PREC_FP32 && cfg->precision != SNB_PREC_TC_F16X2)
@@ -103,6 +103,18 @@ int snb_create(snb_ctx** out, const snb_config* cfg) {
       cudaMalloc(&c->d_frames, c->frame_bytes * c->maxB) != cudaSuccess) {
     snprintf(c->err, sizeof(c->err), "cudaMalloc io staging failed");
     return bail(SNB_ERR_NOMEM);
+  }
+  // asynchronous calls: task_num slots with their own staging buffers + two copy streams
+  cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking);
+  c->slots.resize(std::max(1, std::min(cfg->task_num, 8)));
+  for (auto& sl : c->slots) {
+    if (cudaMalloc(&sl.d_in, c->in_bytes * c->maxB) != cudaSuccess || cudaMalloc(&sl.d_out, c->out_bytes * c->maxB) != cudaSuccess) {
+      snprintf(c->err, sizeof(c->err), "cudaMalloc async staging failed");
+      return bail(SNB_ERR_NOMEM);
+    }
+    cudaEventCreate(&sl.e_in); cudaEventCreate(&sl.e_done);
+    cudaEventCreateWithFlags(&sl.e_out, cudaEventBlockingSync);
   }
   r = build_plan(c);
   if (r != SNB_OK) return bail(r);
@@ -258,7 +270,11 @@ static int infer_host(snb_ctx* c, const int8_t* in, const uint8_t* frames, int32
 
 int snb_infer(snb_ctx* c, const int8_t* in, int32_t* out, int32_t batch) { return infer_host(c, in, nullptr, out, batch); }
 
-int snb_infer_nv12(snb_ctx* c, const uint8_t* frames, int32_t* out, int32_t batch) { return infer_host(c, nullptr, frames, out, batch); }
+int snb_infer_nv12(snb_ctx* c, const uint8_t* frames, int32_t* out, int32_t batch) {
+  // NV12 has 2x2 chroma blocks: odd model sizes (e.g. KITTI's 375 rows) exist only at the s8 tensor entry points
+  if (c && ((c->H & 1) || (c->W & 1))) return fail(c, SNB_ERR_INVALID, "snb_infer_nv12: NV12 frames need even height and width");
+  return infer_host(c, nullptr, frames, out, batch);
+}
 
 int snb_infer_device(snb_ctx* c, const int8_t* d_in, int32_t* d_out, int32_t batch, void* cuda_stream) {
   if (!c || !d_in || !d_out || batch < 1) return fail(c, SNB_ERR_INVALID, "snb_infer_device: bad arguments");
@@ -396,17 +412,83 @@ int snb_profile_pass(snb_ctx* c, int32_t batch, snb_kernel_time* out, int32_t ca
 
 }  // extern "C"
 
+// Retire the oldest in-flight call: wait for its device->host copy, fire the callback, free its task slot.
+static void retire_oldest(snb_ctx* c) {
+  AsyncSlot& sl = c->slots[c->n_ret % c->slots.size()];
+  int status = SNB_OK;
+  if (cudaEventSynchronize(sl.e_out) != cudaSuccess) {
+    snprintf(c->err, sizeof(c->err), "async call failed: %s", cudaGetErrorString(cudaGetLastError()));
+    status = SNB_ERR_CUDA;
+  }
+  snb_rt_stat st;
+  {
+    std::lock_guard<std::mutex> run(c->run_mu);
+    float ms = 0.f;
+    if (status == SNB_OK) cudaEventElapsedTime(&ms, sl.e_in, sl.e_done);
+    const double t1 = now_s();
+    c->stat.gpu_ms = ms;
+    c->stat.infer_time_ms = (int)((t1 - sl.t0) * 1e3 + 0.5);
+    c->stat.kernel_launches = (int)c->ops.size() + 2;
+    c->fps_in += sl.task.batch; c->fps_out += sl.task.batch;
+    c->stat.fps_updated = 0;
+    if (t1 - c->fps_t0 >= 1.0) {
+      c->stat.input_fps = (float)(c->fps_in / (t1 - c->fps_t0));
+      c->stat.output_fps = (float)(c->fps_out / (t1 - c->fps_t0));
+      c->fps_in = c->fps_out = 0; c->fps_t0 = t1; c->stat.fps_updated = 1;
+    }
+    st = c->stat;
+  }
+  if (sl.task.done) sl.task.done(sl.task.user, status, &st);
+  sl.busy = false;
+  ++c->n_ret;
+  {
+    std::unique_lock<std::mutex> lk(c->mu);
+    --c->inflight;
+  }
+  c->cv_push.notify_all();
+}
+
+// Enqueue one call (batch <= max_batch) without waiting for it: H2D on st_in, kernels on the compute stream,
+// D2H on st_out, chained by events.
+static int enqueue_async(snb_ctx* c, const Task& t) {
+  AsyncSlot& sl = c->slots[c->n_enq % c->slots.size()];
+  std::lock_guard<std::mutex> run(c->run_mu);
+  CK(c, cudaSetDevice(c->cfg.device));
+  sl.task = t; sl.t0 = now_s();
+  CK(c, cudaMemcpyAsync(sl.d_in, t.in, c->in_bytes * t.batch, cudaMemcpyHostToDevice, c->st_in));
+  CK(c, cudaEventRecord(sl.e_in, c->st_in));
+  CK(c, cudaStreamWaitEvent(c->stream, sl.e_in, 0));
+  int r = run_chunk(c, t.batch, sl.d_in, nullptr, sl.d_out, c->stream);
+  if (r != SNB_OK) return r;
+  CK(c, cudaEventRecord(sl.e_done, c->stream));
+  CK(c, cudaStreamWaitEvent(c->st_out, sl.e_done, 0));
+  CK(c, cudaMemcpyAsync(t.out, sl.d_out, c->out_bytes * t.batch, cudaMemcpyDeviceToHost, c->st_out));
+  CK(c, cudaEventRecord(sl.e_out, c->st_out));
+  sl.busy = true;
+  ++c->n_enq;
+  return SNB_OK;
+}
+
 static void worker_main(snb_ctx* c) {
   for (;;) {
-    Task t;
+    Task t{};
+    bool have = false;
     {
       std::unique_lock<std::mutex> lk(c->mu);
-      c->cv_pop.wait(lk, [&] { return c->stop || !c->queue.empty(); });
-      if (c->queue.empty()) return;           // stop requested and drained
-      t = c->queue.front();
-      c->queue.pop_front();
+      if (c->n_enq == c->n_ret) c->cv_pop.wait(lk, [&] { return c->stop || !c->queue.empty(); });
+      if (!c->queue.empty()) { t = c->queue.front(); c->queue.pop_front(); have = true; }
+      else if (c->n_enq == c->n_ret) return;   // stop requested, nothing queued, nothing in flight
     }
-    int r = infer_host(c, t.in, nullptr, t.out, t.batch);
+    if (!have) { retire_oldest(c); continue; }  // queue drained: finish what is in flight
+    if (c->n_enq - c->n_ret == c->slots.size()) retire_oldest(c);
+    int r;
+    if (t.batch <= c->maxB) {
+      r = enqueue_async(c, t);
+      if (r == SNB_OK) continue;
+    } else {
+      while (c->n_enq != c->n_ret) retire_oldest(c);   // larger than one pass: chunked synchronous path
+      r = infer_host(c, t.in, nullptr, t.out, t.batch);
+    }
     snb_rt_stat st = c->stat;
     if (t.done) t.done(t.user, r, &st);
     {

@@ -502,6 +502,16 @@ void free_ctx(snb_ctx* c) {
   c->arena.release_all();
   for (void* p : c->wallocs) cudaFree(p);
   c->wallocs.clear();
+  for (auto& sl : c->slots) {
+    if (sl.d_in) cudaFree(sl.d_in);
+    if (sl.d_out) cudaFree(sl.d_out);
+    if (sl.e_in) cudaEventDestroy(sl.e_in);
+    if (sl.e_done) cudaEventDestroy(sl.e_done);
+    if (sl.e_out) cudaEventDestroy(sl.e_out);
+  }
+  c->slots.clear();
+  if (c->st_in) cudaStreamDestroy(c->st_in);
+  if (c->st_out) cudaStreamDestroy(c->st_out);
   if (c->d_in) cudaFree(c->d_in);
   if (c->d_out) cudaFree(c->d_out);
   if (c->d_frames) cudaFree(c->d_frames);

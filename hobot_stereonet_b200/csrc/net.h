@@ -57,6 +57,17 @@ struct Task {
   const int8_t* in; int32_t* out; int batch; snb_done_fn done; void* user;
 };
 
+// One in-flight asynchronous call: its own device staging buffers, so the host->device copy of call k+1 and the
+// device->host copy of call k-1 overlap the kernels of call k (three streams, ordered by events).
+struct AsyncSlot {
+  int8_t* d_in = nullptr;
+  int32_t* d_out = nullptr;
+  cudaEvent_t e_in = nullptr, e_done = nullptr, e_out = nullptr;
+  Task task{};
+  bool busy = false;
+  double t0 = 0;
+};
+
 }  // namespace snb
 
 struct snb_ctx {
@@ -90,6 +101,9 @@ struct snb_ctx {
 
   // async tasks (task_num in flight; callbacks on the worker thread = the reference's PostProcess thread)
   std::thread worker;
+  std::vector<snb::AsyncSlot> slots;   // task_num entries
+  cudaStream_t st_in = nullptr, st_out = nullptr;
+  uint64_t n_enq = 0, n_ret = 0;       // calls enqueued / retired by the worker (slot = n % slots.size())
   std::mutex mu, run_mu;
   std::condition_variable cv_push, cv_pop;
   std::deque<snb::Task> queue;

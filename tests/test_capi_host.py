@@ -94,7 +94,7 @@ def test_create_checks_model_file_first(built_lib):
         Model(64, 96, 3, 8, model_file="/nonexistent/hobot_stereonet.hbm")
     assert e.value.code == capi.SNB_ERR_MODEL and "File is not exist" in str(e.value)
     with pytest.raises(SnbError) as e:
-        Model(63, 96, 3, 8, weights=b"x" * 64)
+        Model(0, 96, 3, 8, weights=b"x" * 64)
     assert e.value.code == capi.SNB_ERR_INVALID
 
 
