@@ -138,6 +138,7 @@ struct CsParams {        // k_conv_stream.cu: streaming convolution, one 32-chan
   int XW, strips, nchunk, rpc, total_units, nxs;
   int relu, res_mode;    // res_mode 0: C8 tensor like out (or none), 1: channel 0 of a C8 tensor, 2: fp32 plane
   uint32_t sub_bytes, slot_bytes, w_bytes;
+  long long* prof;       // SNB_TC_PROF=1: per-CTA cycle counters of the three roles
 };
 struct CsPlan { CsParams p; size_t smem; int num_sms; };
 

@@ -81,7 +81,7 @@ __device__ __forceinline__ void cs_split8(const float* f, uint4& oh, uint4& ol) 
   }
 }
 
-template <int NCO>
+template <int NCO, bool PROF>
 __global__ void __launch_bounds__(CS_THREADS, 1) k_conv_stream(const CsParams p) {
   constexpr int NCOL = 3 * NCO;                // accumulator columns of one job: [ky][NCO]
   constexpr int SLOT_STRIDE = NCO == 32 ? 96 : 64;
@@ -115,18 +115,21 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_conv_stream(const CsParams p)
   const uint32_t tmem_base = tmem_slot;
   const int d = p.dil, zpad = p.kz >> 1;
   const uint32_t wblk = 3 * 2 * 2 * NCOL * 16;              // weight bytes of one (k16, dz): [kx][chunk][2*NCOL][8]
+  long long t_start = 0, tw0 = 0, tw1 = 0, tw2 = 0;
+  if (PROF) t_start = clock64();
+#define CS_WAIT(acc, bar, par) do { if (PROF) { const long long _c = clock64(); mbar_wait(bar, par); acc += clock64() - _c; } else mbar_wait(bar, par); } while (0)
 
   if (warp == 0) {
     // ================================ bulk-copy producer ================================
     const __half* in = static_cast<const __half*>(p.in.p);
-    uint32_t it = 0, nw = 0;
+    uint32_t it = 0, nw = 0, slot = 0, xpar = 1;
     int cur_cc = -1;
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
       const CsUnit un = cs_decode(p, u);
       if (un.nr <= 0) continue;
       if (un.cc != cur_cc) {                                 // (re)load this slice's weights once every MMA reading the old ones retired
         if (lane == 0) {
-          mbar_wait(w_empty, (nw & 1) ^ 1);
+          CS_WAIT(tw0, w_empty, (nw & 1) ^ 1);
           mbar_expect_tx(w_full, p.w_bytes);
           bulk_load(s_w, p.w + (size_t)un.cc * (p.w_bytes / 2), p.w_bytes, w_full);
         }
@@ -138,9 +141,8 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_conv_stream(const CsParams p)
           const int zin = un.d + dz - zpad;
           if (zin < 0 || zin >= p.D) continue;
           for (int k16 = 0; k16 < p.nk16; ++k16, ++it) {
-            const uint32_t slot = it % p.nxs;
             if (lane == 0) {
-              mbar_wait(&x_empty[slot], ((it / p.nxs) & 1) ^ 1);
+              CS_WAIT(tw1, &x_empty[slot], xpar);
               mbar_expect_tx(&x_full[slot], 4 * p.sub_bytes);
             }
             __syncwarp();
@@ -150,58 +152,61 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_conv_stream(const CsParams p)
                                   ((ptrdiff_t)row * p.in.ws + (un.x0 - d)) * 8;
               bulk_load(s_x + (size_t)slot * p.slot_bytes + (size_t)lane * p.sub_bytes, src, p.sub_bytes, &x_full[slot]);
             }
+            if (++slot == (uint32_t)p.nxs) { slot = 0; xpar ^= 1; }
           }
         }
       }
     }
+    if (PROF && lane == 0) { long long* q = p.prof + blockIdx.x * 24; q[0] = clock64() - t_start; q[1] = tw0; q[2] = tw1; q[3] = it; }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
+    // The tensor pipe queues only a few MMAs: uniform-datapath work between two MMA groups is exposed, so the loop
+    // keeps ring positions as counters (no division) and builds descriptors with adds from hoisted bases.
     const bool leader = elect_one();
     const uint32_t idesc = make_idesc_f16(128, NCOL);
     const uint32_t b_lbo = 2 * NCOL * 16;                   // bytes between the two K halves of a weight block
-    const uint32_t dil16 = (uint32_t)d;
-    const uint32_t w_addr = smem_u32(s_w);
-    uint32_t it = 0, nj = 0, nw = 0;
+    const uint64_t dil16 = (uint64_t)d;
+    const uint64_t a_desc0 = make_smem_desc(smem_u32(s_x), p.sub_bytes, 128);     // ring slot 0, hi plane
+    const uint64_t a_lo_off = (uint64_t)(2 * p.sub_bytes >> 4), a_slot16 = (uint64_t)(p.slot_bytes >> 4);
+    const uint64_t w_desc0 = make_smem_desc(smem_u32(s_w), b_lbo, 128);
+    const uint64_t wblk16 = (uint64_t)(wblk >> 4), wkx16 = (uint64_t)(2 * b_lbo >> 4);
+    uint32_t slot = 0, xpar = 0, ts = 0, spar = 1, nw = 0;
     int cur_cc = -1;
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
       const CsUnit un = cs_decode(p, u);
       if (un.nr <= 0) continue;
-      if (un.cc != cur_cc) { mbar_wait(w_full, nw & 1); cur_cc = un.cc; ++nw; }
-      for (int j = 0; j < un.nr + 2; ++j, ++nj) {
-        const uint32_t ts = nj % CS_SLOTS;
-        mbar_wait(&s_empty[ts], ((nj / CS_SLOTS) & 1) ^ 1);
+      if (un.cc != cur_cc) { CS_WAIT(tw0, w_full, nw & 1); cur_cc = un.cc; ++nw; }
+      const int dz0 = un.d - zpad < 0 ? zpad - un.d : 0, dz1 = un.d + p.kz - 1 - zpad >= p.D ? p.D - 1 - un.d + zpad : p.kz - 1;
+      for (int j = 0; j < un.nr + 2; ++j) {
+        CS_WAIT(tw1, &s_empty[ts], spar);
         const uint32_t dcol = tmem_base + ts * SLOT_STRIDE;
-        bool first = true;
-        for (int dz = 0; dz < p.kz; ++dz) {
-          const int zin = un.d + dz - zpad;
-          if (zin < 0 || zin >= p.D) continue;
-          for (int k16 = 0; k16 < p.nk16; ++k16, ++it) {
-            const uint32_t slot = it % p.nxs;
-            mbar_wait(&x_full[slot], (it / p.nxs) & 1);
+        uint32_t acc = 0;
+        for (int dz = dz0; dz <= dz1; ++dz) {
+          uint64_t w_hi = w_desc0 + (uint64_t)dz * wblk16;
+          for (int k16 = 0; k16 < p.nk16; ++k16, w_hi += (uint64_t)p.kz * wblk16) {
+            CS_WAIT(tw2, &x_full[slot], xpar);
             tc_fence_after();
+            const uint64_t a_hi = a_desc0 + (uint64_t)slot * a_slot16, a_lo = a_hi + a_lo_off;
             if (leader) {
-              const uint32_t a_addr = smem_u32(s_x + (size_t)slot * p.slot_bytes);
-              const uint64_t a_hi = make_smem_desc(a_addr, p.sub_bytes, 128);
-              const uint64_t a_lo = make_smem_desc(a_addr + 2 * p.sub_bytes, p.sub_bytes, 128);
-              const uint32_t wb = w_addr + (uint32_t)(k16 * p.kz + dz) * wblk;
-#pragma unroll
-              for (int kx = 0; kx < 3; ++kx) {
-                const uint64_t w_hi = make_smem_desc(wb + (uint32_t)(kx * 2) * b_lbo, b_lbo, 128);
-                const uint64_t w_lo = w_hi + (uint64_t)NCOL;            // + NCOL rows x 16 B
-                const uint64_t sh = (uint64_t)(kx * dil16);
-                if (first && kx == 0) umma_f16_zero(dcol, a_hi, w_hi, idesc);
-                else umma_f16_acc(dcol, a_hi + sh, w_hi, idesc);
-                umma_f16_acc(dcol, a_hi + sh, w_lo, idesc);
-                umma_f16_acc(dcol, a_lo + sh, w_hi, idesc);
-              }
+              umma_f16(dcol, a_hi, w_hi, idesc, acc);
+              umma_f16_acc(dcol, a_hi, w_hi + NCOL, idesc);
+              umma_f16_acc(dcol, a_lo, w_hi, idesc);
+              umma_f16_acc(dcol, a_hi + dil16, w_hi + wkx16, idesc);
+              umma_f16_acc(dcol, a_hi + dil16, w_hi + wkx16 + NCOL, idesc);
+              umma_f16_acc(dcol, a_lo + dil16, w_hi + wkx16, idesc);
+              umma_f16_acc(dcol, a_hi + 2 * dil16, w_hi + 2 * wkx16, idesc);
+              umma_f16_acc(dcol, a_hi + 2 * dil16, w_hi + 2 * wkx16 + NCOL, idesc);
+              umma_f16_acc(dcol, a_lo + 2 * dil16, w_hi + 2 * wkx16, idesc);
               umma_commit(&x_empty[slot]);
             }
             __syncwarp();
-            first = false;
+            acc = 1;
+            if (++slot == (uint32_t)p.nxs) { slot = 0; xpar ^= 1; }
           }
         }
         if (leader) umma_commit(&s_full[ts]);
         __syncwarp();
+        if (++ts == CS_SLOTS) { ts = 0; spar ^= 1; }
       }
       // the next unit of this CTA needs other weights: tell the producer when the MMAs above have retired
       int un_next = u + gridDim.x;
@@ -211,6 +216,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_conv_stream(const CsParams p)
         __syncwarp();
       }
     }
+    if (PROF && lane == 0) { long long* q = p.prof + blockIdx.x * 24; q[8] = clock64() - t_start; q[9] = tw0; q[10] = tw1; q[11] = tw2; q[12] = 0; }
   } else {
     // ================================ epilogue ================================
     const int m = (warp & 3) * 32 + lane;
@@ -250,7 +256,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_conv_stream(const CsParams p)
               rl[cb] = __ldg(reinterpret_cast<const uint4*>(rp + (size_t)cb * p.D * p.res.slice + p.res.lo));
             }
           }
-          mbar_wait(&s_full[ts], (nj / CS_SLOTS) & 1);
+          CS_WAIT(tw0, &s_full[ts], (nj / CS_SLOTS) & 1);
           tc_fence_after();
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
@@ -309,7 +315,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_conv_stream(const CsParams p)
           } else if (ok && p.res_mode == 2) {
             r = __ldg(p.res_plane + o);
           }
-          mbar_wait(&s_full[ts], (nj / CS_SLOTS) & 1);
+          CS_WAIT(tw0, &s_full[ts], (nj / CS_SLOTS) & 1);
           tc_fence_after();
           float v0[16], v1[16], v2[16];
           const uint32_t col = lane_addr + ts * SLOT_STRIDE;
@@ -329,6 +335,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_conv_stream(const CsParams p)
     }
   }
 
+  if (PROF && warp == 2 && lane == 0) { long long* q = p.prof + blockIdx.x * 24; q[16] = clock64() - t_start; q[17] = tw0; }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
@@ -382,15 +389,33 @@ cudaError_t conv_stream_plan(CsPlan* plan, const Tens& in, int cin, int cout, in
 }
 
 template <int NCO>
-static cudaError_t cs_launch_t(const CsParams& p, int grid, size_t smem, cudaStream_t st) {
+static cudaError_t cs_launch_t(CsParams p, int grid, size_t smem, cudaStream_t st) {
   static bool attr_done[32] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 31]) {
-    cudaFuncSetAttribute(k_conv_stream<NCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    cudaFuncSetAttribute(k_conv_stream<NCO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    cudaFuncSetAttribute(k_conv_stream<NCO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
     attr_done[dev & 31] = true;
   }
-  return launch_k(k_conv_stream<NCO>, grid, CS_THREADS, smem, st, p);
+  static const int prof = getenv("SNB_TC_PROF") ? atoi(getenv("SNB_TC_PROF")) : 0;
+  if (!prof) return launch_k(k_conv_stream<NCO, false>, grid, CS_THREADS, smem, st, p);
+  // diagnostics only: per-role cycle counters, synchronous read-back, max over CTAs
+  static long long* d_prof = nullptr;
+  if (!d_prof) cudaMalloc(&d_prof, 256 * 24 * sizeof(long long));
+  p.prof = d_prof;
+  cudaMemsetAsync(d_prof, 0, 256 * 24 * sizeof(long long), st);
+  cudaError_t e = launch_k(k_conv_stream<NCO, true>, grid, CS_THREADS, smem, st, p);
+  cudaStreamSynchronize(st);
+  std::vector<long long> h(grid * 24);
+  cudaMemcpy(h.data(), d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+  long long mx[24] = {0};
+  for (int b = 0; b < grid; ++b) for (int k = 0; k < 24; ++k) mx[k] = std::max(mx[k], h[b * 24 + k]);
+  fprintf(stderr, "[csprof] H%d W%d D%d Cin%d nco%d ccs%d kz%d dil%d N%d units %d (rpc %d) grid %d nxs %d w_bytes %u | producer total %lld wait_w_empty %lld wait_x_empty %lld entries %lld | "
+          "issuer total %lld wait_w %lld wait_slot %lld wait_x %lld jobs %lld | epilogue total %lld wait_full %lld\n",
+          p.H, p.W, p.D, p.nk16 * 16, p.nco, p.ccs, p.kz, p.dil, p.N, p.total_units, p.rpc, grid, p.nxs, p.w_bytes,
+          mx[0], mx[1], mx[2], mx[3], mx[8], mx[9], mx[10], mx[11], mx[12], mx[16], mx[17]);
+  return e;
 }
 
 cudaError_t launch_conv_stream(const CsPlan& plan, int N, const void* w, const float* bias, const Tens* out, const Tens* res,

@@ -166,17 +166,21 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
     const uint32_t dil16 = (uint32_t)d;                     // descriptor address units of 16 B = one pixel
     const uint32_t wa_addr = smem_u32(s_wa), wb_addr = smem_u32(s_wb);
     mbar_wait(w_full, 0);
-    uint32_t na = 0, nb = 0, itx = 0;
+    // The tensor pipe queues only a few MMAs, so uniform-datapath work between two jobs is exposed: ring positions
+    // are counters (no division), descriptors are adds on hoisted bases.
+    const uint64_t x_desc0 = make_smem_desc(smem_u32(s_x), p.sub_bytes, 128), y_desc0 = make_smem_desc(smem_u32(s_y), p.sub_bytes, 128);
+    const uint64_t wa_desc0 = make_smem_desc(wa_addr, b_lbo, 128), wb_desc0 = make_smem_desc(wb_addr, b_lbo, 128);
+    const uint64_t slot16 = (uint64_t)(p.slot_bytes >> 4), sub16 = (uint64_t)(p.sub_bytes >> 4), wkx16 = (uint64_t)(2 * b_lbo >> 4);
+    uint32_t xs = 0, xpar = 0, ys = 0, ypar = 0, apar = 1, bpar = 1, njobs = 0;
 
-    // 12 MMAs of one job: A rows from `a_addr` ([plane][chunk][px][8]), weights from `w_addr`
-    auto issue_job = [&](uint32_t a_addr, uint32_t w_addr, uint32_t dcol) {
+    // 12 MMAs of one job: A rows at descriptor `a` ([plane][chunk][px][8]), weights at descriptor `w`
+    auto issue_job = [&](uint64_t a, uint64_t w, uint32_t dcol) {
 #pragma unroll
       for (int k16 = 0; k16 < 2; ++k16) {
-        const uint64_t a_hi = make_smem_desc(a_addr + (uint32_t)(2 * k16) * p.sub_bytes, p.sub_bytes, 128);
-        const uint64_t a_lo = make_smem_desc(a_addr + (uint32_t)(4 + 2 * k16) * p.sub_bytes, p.sub_bytes, 128);
+        const uint64_t a_hi = a + (uint64_t)(2 * k16) * sub16, a_lo = a_hi + 4 * sub16;
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const uint64_t db = make_smem_desc(w_addr + (uint32_t)((k16 * 3 + kx) * 2) * b_lbo, b_lbo, 128);
+          const uint64_t db = w + (uint64_t)(k16 * 3 + kx) * wkx16;
           const uint64_t sh = (uint64_t)(kx * dil16);
           if (k16 == 0 && kx == 0) umma_f16_zero(dcol, a_hi, db, idesc1);
           else umma_f16_acc(dcol, a_hi + sh, db, idesc1);
@@ -190,36 +194,36 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
       if (un.nr <= 0) continue;
       for (int step = 0; step < un.nr + 5; ++step) {
         if (step < un.nr + 4) {                            // a-job: x row i0 - 2 + step
-          const uint32_t slot = itx % p.nxs, ts = na % RB_ASLOTS;
-          RB_WAIT(tw0, &x_full[slot], (itx / p.nxs) & 1);
-          RB_WAIT(tw1, &sa_empty[ts], ((na / RB_ASLOTS) & 1) ^ 1);
+          RB_WAIT(tw0, &x_full[xs], xpar);
+          RB_WAIT(tw1, &sa_empty[0], apar);
           tc_fence_after();
           if (leader) {
-            issue_job(smem_u32(s_x + (size_t)slot * p.slot_bytes), wa_addr, tmem_base + ts * RB_SLOT_COLS);
-            umma_commit(&sa_full[ts]);
-            umma_commit(&x_empty[slot]);
+            issue_job(x_desc0 + (uint64_t)xs * slot16, wa_desc0, tmem_base);
+            umma_commit(&sa_full[0]);
+            umma_commit(&x_empty[xs]);
           }
           __syncwarp();
-          ++itx; ++na;
+          if (++xs == (uint32_t)p.nxs) { xs = 0; xpar ^= 1; }
+          apar ^= 1; ++njobs;
         }
         if (step >= 3 && step - 3 < un.nr + 2) {           // b-job: y row i0 - 1 + (step - 3)
-          const uint32_t ys = nb % RB_YSLOTS, ts = nb % RB_BSLOTS;
-          RB_WAIT(tw2, &y_full[ys], (nb / RB_YSLOTS) & 1);
-          RB_WAIT(tw3, &sb_empty[ts], ((nb / RB_BSLOTS) & 1) ^ 1);
+          RB_WAIT(tw2, &y_full[ys], ypar);
+          RB_WAIT(tw3, &sb_empty[0], bpar);
           tc_fence_after();
           if (leader) {
-            issue_job(smem_u32(s_y + (size_t)ys * p.slot_bytes), wb_addr, tmem_base + (RB_ASLOTS + ts) * RB_SLOT_COLS);
-            umma_commit(&sb_full[ts]);
+            issue_job(y_desc0 + (uint64_t)ys * slot16, wb_desc0, tmem_base + RB_SLOT_COLS);
+            umma_commit(&sb_full[0]);
             umma_commit(&y_empty[ys]);
           }
           __syncwarp();
-          ++nb;
+          if (++ys == RB_YSLOTS) { ys = 0; ypar ^= 1; }
+          bpar ^= 1; ++njobs;
         }
       }
     }
     if (PROF && lane == 0) {
       long long* q = p.prof + blockIdx.x * 24;
-      q[0] = clock64() - t_start; q[1] = tw0; q[2] = tw1; q[3] = tw2; q[4] = tw3; q[5] = na + nb;
+      q[0] = clock64() - t_start; q[1] = tw0; q[2] = tw1; q[3] = tw2; q[4] = tw3; q[5] = njobs;
     }
   } else if (warp < 2 + RB_GROUP_WARPS) {
     // ================================ epilogue group A: a-jobs -> y rows ================================

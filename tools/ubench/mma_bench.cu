@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(128, 1) k_bench(int shift16, int iters, int mo
     const uint32_t idesc = make_idesc_f16(128, N);
     uint64_t da0, db0;
     if (mode == 0) { da0 = make_smem_desc(sa, 32 * 1024, 128); db0 = make_smem_desc(sb, 8 * 1024, 128); }
+    else if (mode == 2) { da0 = make_smem_desc(sa, 2080, 128); db0 = make_smem_desc(sb, 3072, 128); }   // the conv kernels' strides
     else { da0 = make_desc_sw128(sa); db0 = make_desc_sw128(sb); }
     const uint64_t da1 = da0 + (uint32_t)shift16, da2 = da0 + (uint32_t)(2 * shift16);
     for (int a = 0; a < NACC; ++a) umma_f16(tm + a * N, da0, db0, idesc, 0u);
@@ -107,6 +108,10 @@ int main() {
   run<32, 8>(sms, 1, 0, "16 B", d); run<32, 8>(sms, 130, 0, "130 px", d); run<32, 8>(sms, 8, 0, "128 B", d);
   run<64, 8>(sms, 1, 0, "16 B", d); run<64, 8>(sms, 130, 0, "130 px", d); run<64, 8>(sms, 8, 0, "128 B", d);
   run<128, 4>(sms, 1, 0, "16 B", d); run<256, 2>(sms, 1, 0, "16 B", d);
+  printf("# N = 48 / 96 / 192 (the conv kernels' shapes), aligned and 16 B-shifted windows, benchmark and kernel strides\n");
+  run<48, 8>(sms, 0, 0, "", d); run<96, 4>(sms, 0, 0, "", d); run<192, 2>(sms, 0, 0, "", d);
+  run<48, 8>(sms, 1, 0, "16 B", d); run<96, 4>(sms, 1, 0, "16 B", d); run<192, 2>(sms, 1, 0, "16 B", d);
+  run<96, 4>(sms, 1, 2, "16 B, LBO 2080/3072", d); run<192, 2>(sms, 1, 2, "16 B, LBO 2080/3072", d); run<96, 1>(sms, 1, 2, "one accumulator", d);
   printf("# 128B-swizzle layout for comparison\n");
   run<32, 1>(sms, 0, 1, "", d); run<32, 8>(sms, 0, 1, "", d); run<64, 8>(sms, 0, 1, "", d); run<128, 4>(sms, 0, 1, "", d); run<256, 2>(sms, 0, 1, "", d);
   return 0;
