@@ -248,34 +248,36 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
         tc_fence_after();
         if (ja >= 2) RB_WAIT(tw1, &y_empty[ys], ((ny / RB_YSLOTS) & 1) ^ 1);
         const long long c0 = PROF ? clock64() : 0;
+        // drain first (the finished row goes to f, the partial rows roll over), hand the slot back, then emit
+        float f[32];
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           const uint32_t col = lane_addr + ts * RB_SLOT_COLS + hf * 48;
           float v[16];
           rb_ld_sum(col + 32, v);              // kernel row 2 completes the oldest partial row
-          if (ja >= 2) {
 #pragma unroll
-            for (int jb = 0; jb < 2; ++jb) {
-              float f[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = ok ? fmaxf(a0[hf * 16 + jb * 8 + j] + v[jb * 8 + j], 0.f) : 0.f;
-              uint4 oh, ol;
-              rb_split8(f, oh, ol);
-              const uint32_t a = sy_addr + ys * p.slot_bytes + (uint32_t)(hf * 2 + jb) * p.sub_bytes;
-              rb_sts16(a, oh);
-              rb_sts16(a + 4 * p.sub_bytes, ol);
-            }
-          }
+          for (int c = 0; c < 16; ++c) f[hf * 16 + c] = a0[hf * 16 + c] + v[c];
           rb_ld_sum(col + 16, v);
 #pragma unroll
           for (int c = 0; c < 16; ++c) a0[hf * 16 + c] = a1[hf * 16 + c] + v[c];
           rb_ld_sum(col, v);
 #pragma unroll
           for (int c = 0; c < 16; ++c) a1[hf * 16 + c] = v[c] + s_bias[hf * 16 + c];
-          if (hf == 1) {                       // the slot is in registers: hand it back to the issuer
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sa_empty[ts]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sa_empty[ts]);
+        if (ja >= 2) {
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb) {
+            float g[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) g[q] = ok ? fmaxf(f[cb * 8 + q], 0.f) : 0.f;
+            uint4 oh, ol;
+            rb_split8(g, oh, ol);
+            const uint32_t a = sy_addr + ys * p.slot_bytes + (uint32_t)cb * p.sub_bytes;
+            rb_sts16(a, oh);
+            rb_sts16(a + 4 * p.sub_bytes, ol);
           }
         }
         if (ja >= 2) {
