@@ -3,6 +3,7 @@
 // choices are documented in DESIGN.md §2 and restated identically in oracle/stereonet_ref.py.
 #include "net.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -202,9 +203,11 @@ struct Builder {
   bool stream_ok(const ConvW& cw, const Tens& in, int stride, int dil, CsPlan* plan) const {
     if (c->planes != 2 || (c->cfg.flags & (SNB_FLAG_NO_TENSOR | SNB_FLAG_NO_STREAM)) || stride != 1 || cw.ks != 3) return false;
     if (conv_stream_plan(plan, in, cw.cin, cw.cout, dil, cw.kz, c->num_sms) != cudaSuccess) return false;
-    // measured on config 2 (profiles/): resident weights pay off while one slice stays under ~80 KB (firstconv.1 29 vs 39 us,
-    // layer2 equal, conv_out 41 vs 52, conv3d_alone 44 vs 64); above that the staged k_conv_tc tiles win (layer3/4 28 vs 32 us)
-    return cw.cout == 1 || plan->p.w_bytes <= 80 * 1024;
+    // measured on config 2 (profiles/r01_final_opprof.txt): with the weights of one slice resident the streaming kernel
+    // beats the staged k_conv_tc tiles wherever the slice fits (layer3/4 27 vs 30 us, head.filter.1-4 43 vs 50 us,
+    // firstconv.1 26 vs 39, conv_out 41 vs 52, conv3d_alone 39 vs 64); head.filter.0 (221 KB) and lastconv.0 (295 KB) do not fit
+    static const int max_kb = getenv("SNB_STREAM_MAX_KB") ? atoi(getenv("SNB_STREAM_MAX_KB")) : 160;
+    return cw.cout == 1 || plan->p.w_bytes <= (uint32_t)max_kb * 1024;
   }
 
   // out = ReLU(conv_b(ReLU(conv_a(in))) + res) with 32 channels, as ONE launch when the tcgen05 path allows it
