@@ -136,6 +136,7 @@ struct CsParams {        // k_conv_stream.cu: streaming convolution, one 32-chan
   int N, D, H, W, dil, kz, nk16, in_pad;
   int nco, ccs;          // output channels per unit (32, or 16 with one real channel), number of slices
   int XW, strips, nchunk, rpc, total_units, nxs;
+  int nslots, tmem_cols; // TMEM accumulator slots / allocated columns (5 / 512, or 2 / 256 in the two-CTAs-per-SM configuration)
   int relu, res_mode;    // res_mode 0: C8 tensor like out (or none), 1: channel 0 of a C8 tensor, 2: fp32 plane
   uint32_t sub_bytes, slot_bytes, w_bytes;
   long long* prof;       // SNB_TC_PROF=1: per-CTA cycle counters of the three roles
@@ -147,10 +148,10 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // Programmatic dependent launch: every kernel of the pass is launched with the stream-serialization attribute and
 // calls pdl_trigger() + pdl_wait() before it touches global memory written by its predecessors, so the next
 // kernel's launch latency and prologue (barrier init, TMEM allocation, weight staging) overlap the current kernel's
-// tail.  Captured into the CUDA graph as programmatic edges.  Opt-in (SNB_PDL=1): measured gain on config 2 is
-// 0.6 % (2.167 vs 2.180 ms/step) because the captured graph already runs the kernels back to back.
+// tail.  Captured into the CUDA graph as programmatic edges.  On by default (SNB_PDL=0 turns it off); it pays where
+// two CTAs of consecutive kernels fit on one SM (k_conv_stream's small configuration).
 inline bool pdl_enabled() {
-  static const bool on = getenv("SNB_PDL") && atoi(getenv("SNB_PDL"));
+  static const bool on = !getenv("SNB_PDL") || atoi(getenv("SNB_PDL"));
   return on;
 }
 template <typename... KArgs, typename... Args>

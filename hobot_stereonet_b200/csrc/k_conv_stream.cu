@@ -29,7 +29,7 @@ using namespace ptx;
 
 constexpr int CS_THREADS = 192;
 constexpr int CS_EPI_WARPS = 4;
-constexpr int CS_SLOTS = 5;
+constexpr int CS_SLOTS = 5;                     // TMEM slots of the large configuration (the co-resident one uses 2)
 
 struct CsUnit { int cc, n, d, x0, c, i0, nr; };
 
@@ -81,8 +81,8 @@ __device__ __forceinline__ void cs_split8(const float* f, uint4& oh, uint4& ol) 
   }
 }
 
-template <int NCO, bool PROF>
-__global__ void __launch_bounds__(CS_THREADS, 1) k_conv_stream(const CsParams p) {
+template <int NCO, bool PROF, int MINB>
+__global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams p) {
   constexpr int NCOL = 3 * NCO;                // accumulator columns of one job: [ky][NCO]
   constexpr int SLOT_STRIDE = NCO == 32 ? 96 : 64;
   extern __shared__ uint8_t smem_raw[];
@@ -105,8 +105,16 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_conv_stream(const CsParams p)
     for (int i = 0; i < p.nxs; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
     for (int i = 0; i < CS_SLOTS; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], CS_EPI_WARPS); }
     fence_barrier_init();
+    // the first unit's weights are constants of the pass: stage them before waiting on the previous kernel, so that
+    // under programmatic dependent launch (two of these CTAs fit on one SM) the load overlaps the predecessor's tail
+    int u0 = blockIdx.x;
+    while (u0 < p.total_units && cs_decode(p, u0).nr <= 0) u0 += gridDim.x;
+    if (u0 < p.total_units) {
+      mbar_expect_tx(w_full, p.w_bytes);
+      bulk_load(s_w, p.w + (size_t)cs_decode(p, u0).cc * (p.w_bytes / 2), p.w_bytes, w_full);
+    }
   }
-  if (warp == 1) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(&tmem_slot, p.tmem_cols); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -128,7 +136,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_conv_stream(const CsParams p)
       const CsUnit un = cs_decode(p, u);
       if (un.nr <= 0) continue;
       if (un.cc != cur_cc) {                                 // (re)load this slice's weights once every MMA reading the old ones retired
-        if (lane == 0) {
+        if (lane == 0 && nw > 0) {                           // (the first slice was staged in the prologue)
           CS_WAIT(tw0, w_empty, (nw & 1) ^ 1);
           mbar_expect_tx(w_full, p.w_bytes);
           bulk_load(s_w, p.w + (size_t)un.cc * (p.w_bytes / 2), p.w_bytes, w_full);
@@ -206,7 +214,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_conv_stream(const CsParams p)
         }
         if (leader) umma_commit(&s_full[ts]);
         __syncwarp();
-        if (++ts == CS_SLOTS) { ts = 0; spar ^= 1; }
+        if (++ts == (uint32_t)p.nslots) { ts = 0; spar ^= 1; }
       }
       // the next unit of this CTA needs other weights: tell the producer when the MMAs above have retired
       int un_next = u + gridDim.x;
@@ -221,7 +229,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_conv_stream(const CsParams p)
     // ================================ epilogue ================================
     const int m = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    uint32_t nj = 0;
+    uint32_t ts = 0, fpar = 0;
     int cur_cc = -1;
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
       const CsUnit un = cs_decode(p, u);
@@ -243,8 +251,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_conv_stream(const CsParams p)
         for (int c = 0; c < 32; ++c) a0[c] = a1[c] = 0.f;
         const size_t o_base = (size_t)un.n * p.out.ss + ((size_t)(un.cc * 4) * p.D + un.d) * p.out.slice + (size_t)opx * 8;
         const size_t r_base = (size_t)un.n * p.res.ss + ((size_t)(un.cc * 4) * p.D + un.d) * p.res.slice + (size_t)opx * 8;
-        for (int j = 0; j < un.nr + 2; ++j, ++nj) {
-          const uint32_t ts = nj % CS_SLOTS;
+        for (int j = 0; j < un.nr + 2; ++j) {
           const int row = un.c + d * (un.i0 - 2 + j);       // the output row this job completes
           const bool ok = col_ok && j >= 2 && row < p.H;
           uint4 rh[4], rl[4];
@@ -256,17 +263,19 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_conv_stream(const CsParams p)
               rl[cb] = __ldg(reinterpret_cast<const uint4*>(rp + (size_t)cb * p.D * p.res.slice + p.res.lo));
             }
           }
-          CS_WAIT(tw0, &s_full[ts], (nj / CS_SLOTS) & 1);
+          CS_WAIT(tw0, &s_full[ts], fpar);
           tc_fence_after();
+          const uint32_t ts_cur = ts;
+          if (++ts == (uint32_t)p.nslots) { ts = 0; fpar ^= 1; }
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
             float v0[16], v1[16], v2[16];
-            const uint32_t col = lane_addr + ts * SLOT_STRIDE + hf * 16;
+            const uint32_t col = lane_addr + ts_cur * SLOT_STRIDE + hf * 16;
             cs_ld3x16(col, col + 32, col + 64, v0, v1, v2);
             if (hf == 1) {
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&s_empty[ts]);
+              if (lane == 0) mbar_arrive(&s_empty[ts_cur]);
             }
             if (ok) {
               __half* op = out + o_base + (size_t)row * p.out.ws * 8;
@@ -303,8 +312,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_conv_stream(const CsParams p)
         // single output channel: columns [ky*16 + 0]; fp32 plane out [n][D][H][W], optional residual
         float a0 = 0.f, a1 = 0.f;
         const float bias = s_bias[0];
-        for (int j = 0; j < un.nr + 2; ++j, ++nj) {
-          const uint32_t ts = nj % CS_SLOTS;
+        for (int j = 0; j < un.nr + 2; ++j) {
           const int row = un.c + d * (un.i0 - 2 + j);
           const bool ok = col_ok && j >= 2 && row < p.H;
           float r = 0.f;
@@ -315,7 +323,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_conv_stream(const CsParams p)
           } else if (ok && p.res_mode == 2) {
             r = __ldg(p.res_plane + o);
           }
-          CS_WAIT(tw0, &s_full[ts], (nj / CS_SLOTS) & 1);
+          CS_WAIT(tw0, &s_full[ts], fpar);
           tc_fence_after();
           float v0[16], v1[16], v2[16];
           const uint32_t col = lane_addr + ts * SLOT_STRIDE;
@@ -323,6 +331,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_conv_stream(const CsParams p)
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&s_empty[ts]);
+          if (++ts == (uint32_t)p.nslots) { ts = 0; fpar ^= 1; }
           if (ok) {
             float f = a0 + v2[0] + r;
             if (p.relu) f = fmaxf(f, 0.f);
@@ -338,7 +347,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_conv_stream(const CsParams p)
   if (PROF && warp == 2 && lane == 0) { long long* q = p.prof + blockIdx.x * 24; q[16] = clock64() - t_start; q[17] = tw0; }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
 }
 
 // ---- host side -----------------------------------------------------------------------------------
@@ -378,7 +387,12 @@ cudaError_t conv_stream_plan(CsPlan* plan, const Tens& in, int cin, int cout, in
   p.strips = cdiv(p.W, 128);
   p.w_bytes = (uint32_t)(p.nk16 * kz) * (3 * 2 * 2 * 3 * p.nco * 16);
   plan->num_sms = num_sms;
-  const long avail = 227L * 1024 - 2048 - 128 - (long)p.w_bytes;
+  // Two CTAs per SM (<= 113 KB, 256 TMEM columns each) when the weights are small: with programmatic dependent launch
+  // the next convolution's prologue and weight staging then overlap this one's tail (layer2: 31 back-to-back launches).
+  long budget = 227L * 1024 - 2048;
+  p.nslots = CS_SLOTS; p.tmem_cols = 512;
+  if ((long)p.w_bytes + 128 + 4L * p.slot_bytes <= 112L * 1024 && pdl_enabled()) { budget = 112L * 1024; p.nslots = 2; p.tmem_cols = 256; }
+  const long avail = budget - 128 - (long)p.w_bytes;
   int nxs = avail > 0 ? (int)(avail / p.slot_bytes) : 0;
   nxs = nxs > 16 ? 16 : nxs;
   // the ring must hold more than one job's entries or the producer cannot run ahead of the issuer
@@ -388,33 +402,33 @@ cudaError_t conv_stream_plan(CsPlan* plan, const Tens& in, int cin, int cout, in
   return cudaSuccess;
 }
 
-template <int NCO>
+template <int NCO, int MINB>
 static cudaError_t cs_launch_t(CsParams p, int grid, size_t smem, cudaStream_t st) {
   static bool attr_done[32] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 31]) {
-    cudaFuncSetAttribute(k_conv_stream<NCO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
-    cudaFuncSetAttribute(k_conv_stream<NCO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    cudaFuncSetAttribute(k_conv_stream<NCO, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    cudaFuncSetAttribute(k_conv_stream<NCO, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
     attr_done[dev & 31] = true;
   }
   static const int prof = getenv("SNB_TC_PROF") ? atoi(getenv("SNB_TC_PROF")) : 0;
-  if (!prof) return launch_k(k_conv_stream<NCO, false>, grid, CS_THREADS, smem, st, p);
+  if (!prof) return launch_k(k_conv_stream<NCO, false, MINB>, grid, CS_THREADS, smem, st, p);
   // diagnostics only: per-role cycle counters, synchronous read-back, max over CTAs
   static long long* d_prof = nullptr;
   if (!d_prof) cudaMalloc(&d_prof, 256 * 24 * sizeof(long long));
   p.prof = d_prof;
   cudaMemsetAsync(d_prof, 0, 256 * 24 * sizeof(long long), st);
-  cudaError_t e = launch_k(k_conv_stream<NCO, true>, grid, CS_THREADS, smem, st, p);
+  cudaError_t e = launch_k(k_conv_stream<NCO, true, MINB>, grid, CS_THREADS, smem, st, p);
   cudaStreamSynchronize(st);
   std::vector<long long> h(grid * 24);
   cudaMemcpy(h.data(), d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
   long long mx[24] = {0};
   for (int b = 0; b < grid; ++b) for (int k = 0; k < 24; ++k) mx[k] = std::max(mx[k], h[b * 24 + k]);
-  fprintf(stderr, "[csprof] H%d W%d D%d Cin%d nco%d ccs%d kz%d dil%d N%d units %d (rpc %d) grid %d nxs %d w_bytes %u | producer total %lld wait_w_empty %lld wait_x_empty %lld entries %lld | "
-          "issuer total %lld wait_w %lld wait_slot %lld wait_x %lld jobs %lld | epilogue total %lld wait_full %lld\n",
-          p.H, p.W, p.D, p.nk16 * 16, p.nco, p.ccs, p.kz, p.dil, p.N, p.total_units, p.rpc, grid, p.nxs, p.w_bytes,
-          mx[0], mx[1], mx[2], mx[3], mx[8], mx[9], mx[10], mx[11], mx[12], mx[16], mx[17]);
+  fprintf(stderr, "[csprof] H%d W%d D%d Cin%d nco%d ccs%d kz%d dil%d N%d units %d (rpc %d) grid %d nxs %d slots %d w_bytes %u | producer total %lld wait_w_empty %lld wait_x_empty %lld entries %lld | "
+          "issuer total %lld wait_w %lld wait_slot %lld wait_x %lld | epilogue total %lld wait_full %lld\n",
+          p.H, p.W, p.D, p.nk16 * 16, p.nco, p.ccs, p.kz, p.dil, p.N, p.total_units, p.rpc, grid, p.nxs, p.nslots, p.w_bytes,
+          mx[0], mx[1], mx[2], mx[3], mx[8], mx[9], mx[10], mx[11], mx[16], mx[17]);
   return e;
 }
 
@@ -436,7 +450,9 @@ cudaError_t launch_conv_stream(const CsPlan& plan, int N, const void* w, const f
   p.nchunk = cdiv(rc_max, p.rpc);
   p.total_units = (int)(columns * p.nchunk);
   const int grid = p.total_units < plan.num_sms ? p.total_units : plan.num_sms;
-  cudaError_t e = p.nco == 32 ? cs_launch_t<32>(p, grid, plan.smem, st) : cs_launch_t<16>(p, grid, plan.smem, st);
+  cudaError_t e;
+  if (p.nslots == 2) e = p.nco == 32 ? cs_launch_t<32, 2>(p, grid, plan.smem, st) : cs_launch_t<16, 2>(p, grid, plan.smem, st);
+  else e = p.nco == 32 ? cs_launch_t<32, 1>(p, grid, plan.smem, st) : cs_launch_t<16, 1>(p, grid, plan.smem, st);
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
