@@ -11,6 +11,9 @@
 //   NCO           32: C8 split-fp16 output (+ bias, optional residual, optional ReLU).
 //                 16: single-output-channel convolutions (channel 0 real, 1-15 zero weights: N must be a multiple
 //                     of 16 at M = 128) writing an fp32 plane (+ bias, optional residual, optional ReLU).
+//   stride 2      computed at stride 1, every other row / column stored (firstconv.0/.2, layer2.0): 4x the MMAs of a
+//                 true strided kernel but still 2-3x faster than the CUDA-core path these small layers used before.
+//   1x1           packed as the centre tap of a 3x3 (shortcut convolutions, lastconv.1).
 //   pipeline      warp 0 bulk-copy producer (weights when the channel slice changes, then one ring entry per
 //                 (row, depth tap, 16-channel chunk)), warp 1 TMEM owner + MMA issuer, warps 2-5 epilogue.
 //                 5 TMEM slots decouple the issuer from the epilogue; no end-of-tile burst: every drained job emits
@@ -237,7 +240,7 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
       if (un.cc != cur_cc) {
         // all four epilogue warps use the same 32 biases; a named barrier keeps the refill ordered within the group
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x - 64 < 32) s_bias[threadIdx.x - 64] = (NCO == 32 || threadIdx.x == 64) ? p.bias[un.cc * NCO + (threadIdx.x - 64)] : 0.f;
+        if (threadIdx.x - 64 < 32) s_bias[threadIdx.x - 64] = (int)(threadIdx.x - 64) < p.nbias ? p.bias[un.cc * NCO + (threadIdx.x - 64)] : 0.f;
         asm volatile("bar.sync 1, 128;" ::: "memory");
         cur_cc = un.cc;
       }
@@ -249,11 +252,11 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
         float a0[32], a1[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) a0[c] = a1[c] = 0.f;
-        const size_t o_base = (size_t)un.n * p.out.ss + ((size_t)(un.cc * 4) * p.D + un.d) * p.out.slice + (size_t)opx * 8;
+        const size_t o_base = (size_t)un.n * p.out.ss + ((size_t)(un.cc * 4) * p.D + un.d) * p.out.slice + (size_t)(opx / p.ostride) * 8;
         const size_t r_base = (size_t)un.n * p.res.ss + ((size_t)(un.cc * 4) * p.D + un.d) * p.res.slice + (size_t)opx * 8;
         for (int j = 0; j < un.nr + 2; ++j) {
-          const int row = un.c + d * (un.i0 - 2 + j);       // the output row this job completes
-          const bool ok = col_ok && j >= 2 && row < p.H;
+          const int row = un.c + d * (un.i0 - 2 + j);       // the (stride-1) output row this job completes
+          const bool ok = col_ok && j >= 2 && row < p.H && (p.ostride == 1 || !((row | opx) & 1));
           uint4 rh[4], rl[4];
           if (ok && res) {                                  // residual prefetch while the job's MMAs finish
             const __half* rp = res + r_base + (size_t)row * p.res.ws * 8;
@@ -278,10 +281,11 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
               if (lane == 0) mbar_arrive(&s_empty[ts_cur]);
             }
             if (ok) {
-              __half* op = out + o_base + (size_t)row * p.out.ws * 8;
+              __half* op = out + o_base + (size_t)(row / p.ostride) * p.out.ws * 8;
 #pragma unroll
               for (int jb = 0; jb < 2; ++jb) {
                 const int cb = hf * 2 + jb;
+                if (cb >= p.ncb_out) continue;               // Cout < 32: the slice's upper channel blocks do not exist
                 float f[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) f[q] = a0[hf * 16 + jb * 8 + q] + v2[jb * 8 + q];
@@ -352,15 +356,17 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
 
 // ---- host side -----------------------------------------------------------------------------------
 // Weight packing: [cc][k16][dz][kx][K half][2*3*NCO rows][8]: rows [W_hi: ky*NCO + co | W_lo: 3*NCO + ky*NCO + co]
-void cs_pack_weights(const float* W, int cout, int cin, int kz, int NCO, std::vector<__half>& out) {
-  const int ccs = NCO == 32 ? cout / 32 : 1, nk16 = cin / 16, ncol = 3 * NCO;
+// ks = 1: the single tap lands at the centre (ky = kx = 1) of an otherwise zero 3x3; cin is padded up to a multiple of 16.
+void cs_pack_weights(const float* W, int cout, int cin, int kz, int ks, int NCO, std::vector<__half>& out) {
+  const int ccs = NCO == 32 ? (cout + 31) / 32 : 1, nk16 = (cin + 15) / 16, ncol = 3 * NCO;
   out.assign((size_t)ccs * nk16 * kz * 3 * 2 * 2 * ncol * 8, __float2half(0.f));
   for (int co = 0; co < cout; ++co)
     for (int ci = 0; ci < cin; ++ci)
       for (int dz = 0; dz < kz; ++dz)
         for (int ky = 0; ky < 3; ++ky)
           for (int kx = 0; kx < 3; ++kx) {
-            const float v = W[((((size_t)co * cin + ci) * kz + dz) * 3 + ky) * 3 + kx];
+            if (ks == 1 && (ky != 1 || kx != 1)) continue;
+            const float v = ks == 1 ? W[((size_t)co * cin + ci) * kz + dz] : W[((((size_t)co * cin + ci) * kz + dz) * 3 + ky) * 3 + kx];
             const __half hi = __float2half_rn(v);
             const __half lo = __float2half_rn(v - __half2float(hi));
             const int cc = NCO == 32 ? co / 32 : 0, cl = NCO == 32 ? co % 32 : co;
@@ -373,14 +379,16 @@ void cs_pack_weights(const float* W, int cout, int cin, int kz, int NCO, std::ve
 
 // in: split-fp16 C8 tensor with pad >= dil, cin % 16 == 0.  cout % 32 == 0 (C8 output) or cout == 1 (plane output).
 cudaError_t conv_stream_plan(CsPlan* plan, const Tens& in, int cin, int cout, int dil, int kz, int num_sms) {
-  if (cin % 16 || !(cout % 32 == 0 || cout == 1) || in.planes != 2 || in.pad < dil || dil < 1 || dil > 16 || (kz != 1 && kz != 3))
+  if (cin % 16 || !(cout % 32 == 0 || cout == 1 || (cout < 32 && cout % 8 == 0)) || in.planes != 2 || in.pad < dil || dil < 1 || dil > 16 || (kz != 1 && kz != 3))
     return cudaErrorInvalidValue;
   *plan = CsPlan();
   CsParams& p = plan->p;
   p.in = view(in);
   p.D = in.d; p.H = in.h; p.W = in.w; p.dil = dil; p.kz = kz; p.nk16 = cin / 16; p.in_pad = in.pad;
   p.nco = cout == 1 ? 16 : 32;
-  p.ccs = cout == 1 ? 1 : cout / 32;
+  p.ccs = cout == 1 ? 1 : (cout + 31) / 32;
+  p.ncb_out = cout >= 32 ? 4 : cout / 8;
+  p.nbias = cout == 1 ? 1 : (cout >= 32 ? 32 : cout);
   p.XW = 128 + 2 * dil;
   p.sub_bytes = (uint32_t)p.XW * 16;
   p.slot_bytes = 4 * p.sub_bytes;
@@ -389,14 +397,13 @@ cudaError_t conv_stream_plan(CsPlan* plan, const Tens& in, int cin, int cout, in
   plan->num_sms = num_sms;
   // Two CTAs per SM (<= 113 KB, 256 TMEM columns each) when the weights are small: with programmatic dependent launch
   // the next convolution's prologue and weight staging then overlap this one's tail (layer2: 31 back-to-back launches).
-  long budget = 227L * 1024 - 2048;
-  p.nslots = CS_SLOTS; p.tmem_cols = 512;
-  if ((long)p.w_bytes + 128 + 4L * p.slot_bytes <= 112L * 1024 && pdl_enabled()) { budget = 112L * 1024; p.nslots = 2; p.tmem_cols = 256; }
-  const long avail = budget - 128 - (long)p.w_bytes;
-  int nxs = avail > 0 ? (int)(avail / p.slot_bytes) : 0;
-  nxs = nxs > 16 ? 16 : nxs;
+  auto ring = [&](long budget) { const long avail = budget - 128 - (long)p.w_bytes; int n = avail > 0 ? (int)(avail / p.slot_bytes) : 0; return n > 16 ? 16 : n; };
   // the ring must hold more than one job's entries or the producer cannot run ahead of the issuer
-  if (nxs < 4 || nxs < p.nk16 + 1) return cudaErrorInvalidValue;
+  const int need = std::max(4, p.nk16 + 2);
+  int nxs = pdl_enabled() ? ring(112L * 1024) : 0;
+  p.nslots = 2; p.tmem_cols = 256;
+  if (nxs < need) { nxs = ring(227L * 1024 - 2048); p.nslots = CS_SLOTS; p.tmem_cols = 512; }
+  if (nxs < std::max(4, p.nk16 + 1)) return cudaErrorInvalidValue;
   p.nxs = nxs;
   plan->smem = 128 + (size_t)p.w_bytes + (size_t)nxs * p.slot_bytes;
   return cudaSuccess;
@@ -433,8 +440,9 @@ static cudaError_t cs_launch_t(CsParams p, int grid, size_t smem, cudaStream_t s
 }
 
 cudaError_t launch_conv_stream(const CsPlan& plan, int N, const void* w, const float* bias, const Tens* out, const Tens* res,
-                               float* out_plane, const float* res_plane, int res_c8_ch0, int relu, cudaStream_t st) {
+                               float* out_plane, const float* res_plane, int res_c8_ch0, int relu, int ostride, cudaStream_t st) {
   CsParams p = plan.p;
+  p.ostride = ostride;
   p.N = N; p.w = static_cast<const __half*>(w); p.bias = bias; p.relu = relu;
   if (out) p.out = view(*out);
   p.res_mode = 0;

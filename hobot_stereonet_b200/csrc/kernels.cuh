@@ -22,8 +22,8 @@ cudaError_t launch_resblock_tc(const RbPlan& plan, int N, const void* wa, const 
 // k_conv_stream.cu — streaming tcgen05 convolution, weights resident in shared memory (M1, M3, M5)
 cudaError_t conv_stream_plan(CsPlan* plan, const Tens& in, int cin, int cout, int dil, int kz, int num_sms);
 cudaError_t launch_conv_stream(const CsPlan& plan, int N, const void* w, const float* bias, const Tens* out, const Tens* res,
-                               float* out_plane, const float* res_plane, int res_c8_ch0, int relu, cudaStream_t st);
-void cs_pack_weights(const float* W, int cout, int cin, int kz, int NCO, std::vector<__half>& out);
+                               float* out_plane, const float* res_plane, int res_c8_ch0, int relu, int ostride, cudaStream_t st);
+void cs_pack_weights(const float* W, int cout, int cin, int kz, int ks, int NCO, std::vector<__half>& out);
 
 // k_mem.cu — HBM-bound kernels
 // P3 tail on device: s8 NCHW [B,6,H,W] -> C8 [2B][1][Hp][Wp][8] (x/128; left n<B, right n>=B; ch 3..7 = 0)

@@ -191,7 +191,7 @@ struct Builder {
     const int key = 100 + nco;
     if (!cw.w_tc.count(key)) {
       std::vector<__half> packed;
-      cs_pack_weights(c->wts[name + ".weight"].data.data(), cw.cout, cw.cin, cw.kz, nco, packed);
+      cs_pack_weights(c->wts[name + ".weight"].data.data(), cw.cout, cw.cin, cw.kz, cw.ks, nco, packed);
       __half* dw = nullptr;
       if (cudaMalloc(&dw, packed.size() * sizeof(__half)) != cudaSuccess) { fail = true; return nullptr; }
       cudaMemcpy(dw, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice);
@@ -201,8 +201,10 @@ struct Builder {
     return cw.w_tc[key];
   }
   bool stream_ok(const ConvW& cw, const Tens& in, int stride, int dil, CsPlan* plan) const {
-    if (c->planes != 2 || (c->cfg.flags & (SNB_FLAG_NO_TENSOR | SNB_FLAG_NO_STREAM)) || stride != 1 || cw.ks != 3) return false;
-    if (conv_stream_plan(plan, in, cw.cin, cw.cout, dil, cw.kz, c->num_sms) != cudaSuccess) return false;
+    if (c->planes != 2 || (c->cfg.flags & (SNB_FLAG_NO_TENSOR | SNB_FLAG_NO_STREAM)) || stride > 2 || (stride == 2 && cw.cout == 1)) return false;
+    // input channels as stored (blocks of 8, zero beyond cin) must be whole 16-channel chunks
+    if (in.cb * 8 < cw.cin || (in.cb * 8) % 16) return false;
+    if (conv_stream_plan(plan, in, in.cb * 8, cw.cout, cw.ks == 1 ? 1 : dil, cw.kz, c->num_sms) != cudaSuccess) return false;
     // measured on config 2 (profiles/r01_final_opprof.txt): with the weights of one slice resident the streaming kernel
     // beats the staged k_conv_tc tiles wherever the slice fits (layer3/4 27 vs 30 us, head.filter.1-4 43 vs 50 us,
     // firstconv.1 26 vs 39, conv_out 41 vs 52, conv3d_alone 39 vs 64); head.filter.0 (221 KB) and lastconv.0 (295 KB) do not fit
@@ -256,8 +258,8 @@ struct Builder {
       const bool has_res = res != nullptr;
       const Tens rt = res ? *res : Tens();
       const int rl = relu ? 1 : 0;
-      op.fn = [splan, nmul, dw, bias, out, has_res, rt, rl](int B, cudaStream_t st) {
-        return launch_conv_stream(splan, nmul * B, dw, bias, &out, has_res ? &rt : nullptr, nullptr, nullptr, 0, rl, st);
+      op.fn = [splan, nmul, dw, bias, out, has_res, rt, rl, stride](int B, cudaStream_t st) {
+        return launch_conv_stream(splan, nmul * B, dw, bias, &out, has_res ? &rt : nullptr, nullptr, nullptr, 0, rl, stride, st);
       };
       op.name += " [tc-stream]";
       ++c->n_tc_convs;
@@ -285,7 +287,7 @@ struct Builder {
     ConvParams p{};
     p.in = view(in); p.out = view(out); p.w = cw.w; p.bias = cw.b;
     if (res) p.res = view(*res);
-    p.CBin = in.cb; p.Din = in.d; p.Hin = in.h; p.Win = in.w;
+    p.CBin = std::min(in.cb, (cw.cin + 7) / 8); p.Din = in.d; p.Hin = in.h; p.Win = in.w;
     p.CBout = out.cb; p.Dout = out.d; p.Hout = ho; p.Wout = wo;
     p.ks = cw.ks; p.kz = cw.kz; p.stride = stride; p.dil = dil; p.relu = relu ? 1 : 0;
     p.half = c->planes == 2;
@@ -302,7 +304,7 @@ struct Builder {
     ConvW& cw = it->second;
     Plane out = palloc(in.d, in.h, in.w);
     CsPlan splan;
-    if (cw.cin % 16 == 0 && stream_ok(cw, in, 1, dil, &splan)) {
+    if (cw.cin % 16 == 0 && cw.ks == 3 && stream_ok(cw, in, 1, dil, &splan)) {
       const __half* dw = stream_weights(name, cw, 16);
       if (!dw) return out;
       const float* bias = cw.b;
@@ -312,7 +314,7 @@ struct Builder {
       float* op_ = out.p;
       Op op; op.name = name + " [tc-stream]";
       op.fn = [splan, dw, bias, op_, has_res, rt, rl](int B, cudaStream_t st) {
-        return launch_conv_stream(splan, B, dw, bias, nullptr, has_res ? &rt : nullptr, op_, nullptr, 1, rl, st);
+        return launch_conv_stream(splan, B, dw, bias, nullptr, has_res ? &rt : nullptr, op_, nullptr, 1, rl, 1, st);
       };
       const double px = (double)in.d * in.h * in.w;
       op.flops = 2.0 * px * cw.cin * 9 * cw.kz;
@@ -347,7 +349,9 @@ int build_plan(snb_ctx* c) {
   const int K = c->K, D = c->D, Hp = c->Hp, Wp = c->Wp, h = c->h, w = c->w;
 
   // input image, C8 [2B][1][Hp][Wp][8]; the pre-process op is issued by the caller (s8 or NV12 source)
-  c->img = b.alloc(2, 3, 1, Hp, Wp, PAD_BACKBONE);
+  // 16 stored channels (3 real) on the tensor-core path: firstconv.0 consumes whole 16-channel K chunks
+  c->img = b.alloc(2, c->planes == 2 ? 16 : 3, 1, Hp, Wp, PAD_BACKBONE);
+  c->img.c = 3;
   Tens img = c->img;
   b.tap("img", img, 2);
 
