@@ -30,7 +30,12 @@ SEED = 1234
 L2_BYTES = 126 * 1024 * 1024
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
 # `ncu --set full` capture (profiles/): filled in by hand after each capture, None when not captured.
-TRAFFIC = {}
+TRAFFIC = {
+    # profiles/r01_final_ncu_full_resblock.csv: one full-resolution refinement block (algorithmic 134 MB)
+    "k_resblock_tc": 106.2e6,
+    # profiles/r01_final_ncu_full_stream.csv: firstconv.0 (algorithmic 33.4 MB in + 16.7 MB out, the output stays in L2)
+    "k_conv_stream": 34.7e6,
+}
 
 
 def synth_inputs(n: int) -> np.ndarray:
