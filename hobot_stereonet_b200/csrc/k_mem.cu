@@ -102,6 +102,7 @@ cudaError_t launch_pre_nv12(const uint8_t* frames, Tens img, int8_t* s8, int B, 
 struct CostvolParams {
   TV gwc, cat, vol;
   int B, D, h, w;
+  int dsplit;            // CTAs sharing one (row, pair, block): each emits D / dsplit hypotheses (more CTAs in flight)
 };
 
 template <typename T>
@@ -109,7 +110,8 @@ __global__ void __launch_bounds__(256) k_costvol(CostvolParams p) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float sm[];
-  const int y = blockIdx.x, b = blockIdx.y, q = blockIdx.z;    // q in 0..3
+  const int y = blockIdx.x, b = blockIdx.y, q = blockIdx.z & 3, dpart = blockIdx.z >> 2;    // q in 0..3
+  const int dper = (p.D + p.dsplit - 1) / p.dsplit, d_lo = dpart * dper, d_hi = min(p.D, d_lo + dper);
   const int w = p.w, h = p.h, D = p.D;
   const int pitch = w * 8 + 4;                                  // +4 floats: 8 blocks hit 8 distinct 16B lanes
   float* sL = sm;                  // [8][pitch]
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(256) k_costvol(CostvolParams p) {
     const float4 l0 = *reinterpret_cast<const float4*>(sL + j * pitch + x * 8);
     const float4 l1 = *reinterpret_cast<const float4*>(sL + j * pitch + x * 8 + 4);
     const float cl = St<T>::ld1(p.cat.p, csrc + e, p.cat.lo);      // unshifted concat value (left blocks)
-    for (int d = 0; d < D; ++d) {
+    for (int d = d_lo; d < d_hi; ++d) {
       float g = 0.f, c = 0.f;
       if (x >= d) {
         const float4 r0 = *reinterpret_cast<const float4*>(sR + j * pitch + (x - d) * 8);
@@ -158,13 +160,14 @@ __global__ void __launch_bounds__(256) k_costvol(CostvolParams p) {
 cudaError_t launch_costvol(Tens gwc, Tens cat, Tens vol, int B, int D, cudaStream_t st) {
   const int h = gwc.h, w = gwc.w;
   const size_t smem = (size_t)2 * 8 * (w * 8 + 4) * sizeof(float);
-  CostvolParams p{view(gwc), view(cat), view(vol), B, D, h, w};
+  const int dsplit = D >= 12 ? 3 : 1;
+  CostvolParams p{view(gwc), view(cat), view(vol), B, D, h, w, dsplit};
   if (vol.planes == 2) {
     if (need_attr(5)) cudaFuncSetAttribute(k_costvol<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    launch_k(k_costvol<__half>, dim3(h, B, 4), 256, smem, st, p);
+    launch_k(k_costvol<__half>, dim3(h, B, 4 * dsplit), 256, smem, st, p);
   } else {
     if (need_attr(2)) cudaFuncSetAttribute(k_costvol<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    launch_k(k_costvol<float>, dim3(h, B, 4), 256, smem, st, p);
+    launch_k(k_costvol<float>, dim3(h, B, 4 * dsplit), 256, smem, st, p);
   }
   return cudaGetLastError();
 }
@@ -179,15 +182,22 @@ __global__ void k_softargmin(const float* __restrict__ cost, float* __restrict__
   if (i >= hw) return;
   const float* c = cost + (size_t)b * D * hw + i;
   float m = -INFINITY, s = 0.f, t = 0.f;
-  for (int d = 0; d < D; ++d) {
-    const float v = __ldg(c + (size_t)d * hw);
-    if (v > m) {
-      const float r = expf(m - v);
-      s *= r; t *= r; m = v;
+  for (int d0 = 0; d0 < D; d0 += 8) {          // 8 independent loads in flight, then the (serial) online-softmax update
+    float v8[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v8[k] = d0 + k < D ? __ldg(c + (size_t)(d0 + k) * hw) : -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float v = v8[k];
+      if (d0 + k >= D) break;
+      if (v > m) {
+        const float r = expf(m - v);
+        s *= r; t *= r; m = v;
+      }
+      const float e = expf(v - m);
+      s += e;
+      t = fmaf(e, (float)(d0 + k), t);
     }
-    const float e = expf(v - m);
-    s += e;
-    t = fmaf(e, (float)d, t);
   }
   disp[(size_t)b * hw + i] = t / s * invD;
 }
@@ -258,7 +268,25 @@ __global__ void k_post_quant(const float* __restrict__ disp, int32_t* __restrict
   out[((size_t)b * H + y) * W + x] = __float2int_rn(disp[((size_t)b * Hp + y) * Wp + x] * qmul);
 }
 
+// four pixels per thread (W % 4 == 0; padded rows are multiples of 4 floats by construction)
+__global__ void k_post_quant4(const float* __restrict__ disp, int32_t* __restrict__ out, int H, int W, int Hp, int Wp,
+                              float qmul) {
+  pdl_trigger();
+  pdl_wait();
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y, b = blockIdx.z;
+  if (x >= W) return;
+  const float4 v = __ldg(reinterpret_cast<const float4*>(disp + ((size_t)b * Hp + y) * Wp + x));
+  int4 q;
+  q.x = __float2int_rn(v.x * qmul); q.y = __float2int_rn(v.y * qmul); q.z = __float2int_rn(v.z * qmul); q.w = __float2int_rn(v.w * qmul);
+  *reinterpret_cast<int4*>(out + ((size_t)b * H + y) * W + x) = q;
+}
+
 cudaError_t launch_post_quant(Plane disp, int32_t* out, int H, int W, float qmul, cudaStream_t st) {
+  if (W % 4 == 0 && disp.w % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    launch_k(k_post_quant4, dim3(cdiv(W, 512), H, disp.n), 128, 0, st, (const float*)disp.p, out, H, W, disp.h, disp.w, qmul);
+    return cudaGetLastError();
+  }
   launch_k(k_post_quant, dim3(cdiv(W, 128), H, disp.n), 128, 0, st, disp.p, out, H, W, disp.h, disp.w, qmul);
   return cudaGetLastError();
 }
