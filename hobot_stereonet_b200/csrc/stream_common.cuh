@@ -1,0 +1,61 @@
+// Helpers shared by the streaming tcgen05 convolution kernels (k_conv_stream.cu, k_conv_chain.cu).
+#pragma once
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace snb {
+
+using namespace ptx;
+
+struct CsUnit { int cc, n, d, x0, c, i0, nr; };
+
+__device__ __forceinline__ CsUnit cs_decode(const CsParams& p, int u) {
+  CsUnit r;
+  const int chunk = u % p.nchunk; u /= p.nchunk;
+  r.c = u % p.dil; u /= p.dil;
+  const int strip = u % p.strips; u /= p.strips;
+  r.d = u % p.D; u /= p.D;
+  r.n = u % p.N;
+  r.cc = u / p.N;                               // slowest index: a CTA rarely changes its weight slice
+  r.x0 = strip * 128;
+  const int rc = r.c < p.H ? (p.H - r.c + p.dil - 1) / p.dil : 0;
+  r.i0 = chunk * p.rpc;
+  r.nr = min(rc, r.i0 + p.rpc) - r.i0;
+  return r;
+}
+
+__device__ __forceinline__ void cs_ld3x16(uint32_t c0, uint32_t c1, uint32_t c2, float (&v0)[16], float (&v1)[16], float (&v2)[16]) {
+  uint32_t r[48];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%48];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%49];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47}, [%50];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
+        "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+        "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47])
+      : "r"(c0), "r"(c1), "r"(c2) : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { v0[i] = __uint_as_float(r[i]); v1[i] = __uint_as_float(r[16 + i]); v2[i] = __uint_as_float(r[32 + i]); }
+}
+
+__device__ __forceinline__ void cs_split8(const float* f, uint4& oh, uint4& ol) {
+  __half2* ph = reinterpret_cast<__half2*>(&oh);
+  __half2* pl = reinterpret_cast<__half2*>(&ol);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __half2 hh = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+    const float2 hf = __half22float2(hh);
+    ph[j] = hh;
+    pl[j] = __floats2half2_rn(f[2 * j] - hf.x, f[2 * j + 1] - hf.y);
+  }
+}
+
+
+}  // namespace snb
