@@ -351,7 +351,10 @@ cudaError_t conv_stream_plan(CsPlan* plan, const Tens& in, int cin, int cout, in
   auto ring = [&](long budget) { const long avail = budget - 128 - (long)p.w_bytes; int n = avail > 0 ? (int)(avail / p.slot_bytes) : 0; return n > 16 ? 16 : n; };
   // the ring must hold more than one job's entries or the producer cannot run ahead of the issuer
   const int need = std::max(4, p.nk16 + 2);
-  int nxs = pdl_enabled() ? ring(112L * 1024) : 0;
+  // opt-in (SNB_STREAM_SMALL=1): measured 567 vs 574 pairs/s at config 2 - two TMEM slots instead of five cost more
+  // than overlapping the next kernel's prologue gains
+  static const bool small_ok = getenv("SNB_STREAM_SMALL") && atoi(getenv("SNB_STREAM_SMALL"));
+  int nxs = pdl_enabled() && small_ok ? ring(112L * 1024) : 0;
   p.nslots = 2; p.tmem_cols = 256;
   if (nxs < need) { nxs = ring(227L * 1024 - 2048); p.nslots = CS_SLOTS; p.tmem_cols = 512; }
   if (nxs < std::max(4, p.nk16 + 1)) return cudaErrorInvalidValue;
