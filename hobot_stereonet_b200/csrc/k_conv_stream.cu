@@ -221,46 +221,49 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
           tc_fence_after();
           const uint32_t ts_cur = ts;
           if (++ts == (uint32_t)p.nslots) { ts = 0; fpar ^= 1; }
+          // drain first (the finished row goes to f, the partial rows roll over), hand the slot back, then emit
+          float f[32];
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
             float v0[16], v1[16], v2[16];
             const uint32_t col = lane_addr + ts_cur * SLOT_STRIDE + hf * 16;
             cs_ld3x16(col, col + 32, col + 64, v0, v1, v2);
-            if (hf == 1) {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&s_empty[ts_cur]);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              f[hf * 16 + c] = a0[hf * 16 + c] + v2[c];
+              a0[hf * 16 + c] = a1[hf * 16 + c] + v1[c];
+              a1[hf * 16 + c] = v0[c] + s_bias[hf * 16 + c];
             }
-            if (ok) {
-              __half* op = out + o_base + (size_t)(row / p.ostride) * p.out.ws * 8;
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[ts_cur]);
+          if (ok) {
+            __half* op = out + o_base + (size_t)(row / p.ostride) * p.out.ws * 8;
 #pragma unroll
-              for (int jb = 0; jb < 2; ++jb) {
-                const int cb = hf * 2 + jb;
-                if (cb >= p.ncb_out) continue;               // Cout < 32: the slice's upper channel blocks do not exist
-                float f[8];
+            for (int cb = 0; cb < 4; ++cb) {
+              if (cb >= p.ncb_out) continue;                 // Cout < 32: the slice's upper channel blocks do not exist
+              float g[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) f[q] = a0[hf * 16 + jb * 8 + q] + v2[jb * 8 + q];
-                if (res) {
-                  const __half2* h2 = reinterpret_cast<const __half2*>(&rh[cb]);
-                  const __half2* l2 = reinterpret_cast<const __half2*>(&rl[cb]);
+              for (int q = 0; q < 8; ++q) g[q] = f[cb * 8 + q];
+              if (res) {
+                const __half2* h2 = reinterpret_cast<const __half2*>(&rh[cb]);
+                const __half2* l2 = reinterpret_cast<const __half2*>(&rl[cb]);
 #pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    const float2 a = __half22float2(h2[q]), b = __half22float2(l2[q]);
-                    f[2 * q] += a.x + b.x; f[2 * q + 1] += a.y + b.y;
-                  }
+                for (int q = 0; q < 4; ++q) {
+                  const float2 a = __half22float2(h2[q]), b = __half22float2(l2[q]);
+                  g[2 * q] += a.x + b.x; g[2 * q + 1] += a.y + b.y;
                 }
-                if (p.relu) {
-#pragma unroll
-                  for (int q = 0; q < 8; ++q) f[q] = fmaxf(f[q], 0.f);
-                }
-                uint4 oh, ol;
-                cs_split8(f, oh, ol);
-                *reinterpret_cast<uint4*>(op + (size_t)cb * p.D * p.out.slice) = oh;
-                *reinterpret_cast<uint4*>(op + (size_t)cb * p.D * p.out.slice + p.out.lo) = ol;
               }
-            }
+              if (p.relu) {
 #pragma unroll
-            for (int c = 0; c < 16; ++c) { a0[hf * 16 + c] = a1[hf * 16 + c] + v1[c]; a1[hf * 16 + c] = v0[c] + s_bias[hf * 16 + c]; }
+                for (int q = 0; q < 8; ++q) g[q] = fmaxf(g[q], 0.f);
+              }
+              uint4 oh, ol;
+              cs_split8(g, oh, ol);
+              *reinterpret_cast<uint4*>(op + (size_t)cb * p.D * p.out.slice) = oh;
+              *reinterpret_cast<uint4*>(op + (size_t)cb * p.D * p.out.slice + p.out.lo) = ol;
+            }
           }
         }
       } else {
