@@ -76,6 +76,7 @@ def load() -> C.CDLL:
         "snb_post_pack": (i64, [vp, u64, vp, u64, vp, u64]),
         "snb_post_parse_depth": (C.c_int, [vp, i64, C.c_float, vp]),
         "snb_weights_synthesize": (i64, [i32, u64, vp, u64]),
+        "snb_post_depth_color": (C.c_int, [vp, vp, i32, C.c_float, vp, vp, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -213,6 +214,14 @@ class Model:
         N, Cc, D, H, W = list(shape)
         a = dst.reshape(N, Cc, D, H, W)
         return a[:, :, 0] if D == 1 else a
+
+    def depth_color(self, q: np.ndarray, alpha: float = 11.0):
+        """ParseTensor on the GPU (parser.cpp:79-118): q int32 [B,1,H,W] host -> (depth f32 [B,H,W], bgr u8 [B,H,W,3])."""
+        B = q.shape[0]
+        depth = np.empty((B, self.H, self.W), np.float32)
+        bgr = np.empty((B, self.H, self.W, 3), np.uint8)
+        self._check(self._l.snb_post_depth_color(self._h, _ptr(np.ascontiguousarray(q, np.int32)), B, alpha, _ptr(depth), _ptr(bgr), 0))
+        return depth, bgr
 
     def profile_pass(self, batch: int = 1):
         arr = (SnbKernelTime * 512)()

@@ -377,6 +377,35 @@ int64_t snb_debug_read(snb_ctx* c, const char* name, float* dst, uint64_t cap, i
   return (int64_t)n;
 }
 
+int snb_post_depth_color(snb_ctx* c, const int32_t* q, int32_t batch, float alpha, float* depth_m, uint8_t* bgr, int32_t is_device) {
+  if (!c || !q || batch < 1 || (!depth_m && !bgr)) return fail(c, SNB_ERR_INVALID, "snb_post_depth_color: bad arguments");
+  std::lock_guard<std::mutex> run(c->run_mu);
+  CK(c, cudaSetDevice(c->cfg.device));
+  cudaStream_t st = c->stream;
+  const size_t n = (size_t)batch * c->H * c->W;
+  const float scale = 2.60443857769133e-06f;
+  if (is_device) {
+    cudaError_t e = launch_post_depth_color(q, depth_m, bgr, n, scale, alpha, st);
+    if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "post_depth_color: %s", cudaGetErrorString(e)); return SNB_ERR_CUDA; }
+    CK(c, cudaStreamSynchronize(st));
+    return SNB_OK;
+  }
+  int32_t* dq = nullptr; float* dd = nullptr; uint8_t* dc = nullptr;
+  auto cleanup = [&] { if (dq) cudaFree(dq); if (dd) cudaFree(dd); if (dc) cudaFree(dc); };
+  if (cudaMalloc(&dq, n * 4) != cudaSuccess || (depth_m && cudaMalloc(&dd, n * 4) != cudaSuccess) || (bgr && cudaMalloc(&dc, n * 3) != cudaSuccess)) {
+    cleanup();
+    return fail(c, SNB_ERR_NOMEM, "snb_post_depth_color: device allocation failed");
+  }
+  cudaError_t e = cudaMemcpyAsync(dq, q, n * 4, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = launch_post_depth_color(dq, dd, dc, n, scale, alpha, st);
+  if (e == cudaSuccess && depth_m) e = cudaMemcpyAsync(depth_m, dd, n * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && bgr) e = cudaMemcpyAsync(bgr, dc, n * 3, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cleanup();
+  if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "snb_post_depth_color: %s", cudaGetErrorString(e)); return SNB_ERR_CUDA; }
+  return SNB_OK;
+}
+
 int snb_profile_pass(snb_ctx* c, int32_t batch, snb_kernel_time* out, int32_t cap) {
   if (!c || batch < 1 || batch > c->maxB) return fail(c, SNB_ERR_INVALID, "snb_profile_pass: bad batch");
   std::lock_guard<std::mutex> run(c->run_mu);

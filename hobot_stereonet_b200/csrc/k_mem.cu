@@ -291,4 +291,39 @@ cudaError_t launch_post_quant(Plane disp, int32_t* out, int H, int W, float qmul
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// what ParseTensor does on the CPU after the model (parser.cpp:79-118), on the GPU:
+//   dis = (float)q * scale;  depth = (float)( (double)(f*B) / ((double)dis * 16.0 * 12.0) / 1000.0 )      [metres]
+//   u8  = cv::convertScaleAbs(depth, alpha)   (float multiply, |.|, round-half-even, saturate; values that do not fit an
+//         int32 - depth = inf at q = 0, NaN - become 0, as cv2 on x86 does via cvtps2dq)
+//   bgr = cv::applyColorMap(u8, COLORMAP_JET)
+// alpha = 11 in parser.cpp:115, 9 in the render tool (publisher_member_function.py:82).
+__constant__ uint8_t c_jet[256][3] = {
+#include "jet_lut.inc"
+};
+
+__global__ void k_post_depth_color(const int32_t* __restrict__ q, float* __restrict__ depth, uint8_t* __restrict__ bgr,
+                                   size_t n, float scale, float alpha) {
+  pdl_trigger();
+  pdl_wait();
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float fb = 527.1931762695312f * 119.89382172f;
+  const float dis = (float)__ldg(q + i) * scale;
+  const float z = (float)((double)fb / ((double)dis * 16.0 * 12.0) / 1000.0);
+  if (depth) depth[i] = z;
+  if (bgr) {
+    const float v = fabsf(z * alpha);
+    int iv = v < 2147483648.f ? __float2int_rn(v) : 0;       // false for NaN too
+    iv = iv > 255 ? 255 : iv;
+    bgr[3 * i] = c_jet[iv][0]; bgr[3 * i + 1] = c_jet[iv][1]; bgr[3 * i + 2] = c_jet[iv][2];
+  }
+}
+
+cudaError_t launch_post_depth_color(const int32_t* q, float* depth, uint8_t* bgr, size_t n, float scale, float alpha,
+                                    cudaStream_t st) {
+  launch_k(k_post_depth_color, dim3((unsigned)((n + 255) / 256)), 256, 0, st, q, depth, bgr, n, scale, alpha);
+  return cudaGetLastError();
+}
+
 }  // namespace snb

@@ -45,4 +45,8 @@ cudaError_t launch_refine_in(Plane disp, Tens img_full, Tens out, int B, cudaStr
 // O1 head: normalised disparity [B][Hp][Wp] -> s32 NCHW [B,1,H,W] (crop), q = rint(dn * qmul)
 cudaError_t launch_post_quant(Plane disp, int32_t* out, int H, int W, float qmul, cudaStream_t st);
 
+// O2 on the GPU (next-row f3): s32 output -> depth in metres (+ JET colour map as cv::convertScaleAbs / applyColorMap)
+cudaError_t launch_post_depth_color(const int32_t* q, float* depth, uint8_t* bgr, size_t n, float scale, float alpha,
+                                    cudaStream_t st);
+
 }  // namespace snb

@@ -160,6 +160,13 @@ SNB_API int64_t snb_post_pack(const int32_t* infer, uint64_t infer_bytes, const 
 /* parser.cpp:79-87 ParseTensor: s32 -> depth in metres (float), f = 527.19..., B = 119.89... mm. */
 SNB_API int snb_post_parse_depth(const int32_t* q, int64_t n, float scale, float* depth_m);
 
+/* parser.cpp:79-118 on the GPU: s32 model output -> depth in metres and the JET colour map
+ * (cv::convertScaleAbs(depth, alpha) + cv::applyColorMap; alpha = 11 in parser.cpp:115, 9 in the render tool).
+ * q: [batch,1,H,W] s32; depth_m: [batch,H,W] f32 or NULL; bgr: [batch,H,W,3] u8 or NULL.  is_device != 0: all three
+ * pointers are device memory and the call only enqueues on the context's stream + synchronises. */
+SNB_API int snb_post_depth_color(snb_ctx* ctx, const int32_t* q, int32_t batch, float alpha, float* depth_m, uint8_t* bgr,
+                                 int32_t is_device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -99,3 +99,15 @@ def parse_tensor_depth_f32(q: np.ndarray, scale: float = OUT_SCALE) -> np.ndarra
     fb = np.float64(np.float32(CAM_F) * np.float32(CAM_B))   # float*float stays float (parser.cpp:86)
     with np.errstate(divide="ignore"):
         return (fb / (dis.astype(np.float64) * 16.0 * 12.0) / 1000.0).astype(np.float32)
+
+
+def render_depth_colormap(q: np.ndarray, alpha: float = 11.0, scale: float = OUT_SCALE):
+    """parser.cpp:79-118 (alpha = 11) / publisher_member_function.py:81-82 (alpha = 9): depth in metres, then
+    cv::convertScaleAbs(depth, alpha) and cv::applyColorMap(COLORMAP_JET), through the very cv2 functions the
+    reference calls.  q [..., H, W] int32 -> (depth float32 [..., H, W], bgr uint8 [..., H, W, 3])."""
+    import cv2
+    depth = parse_tensor_depth_f32(q, scale)
+    flat = depth.reshape(-1, depth.shape[-1])
+    u8 = cv2.convertScaleAbs(flat, alpha=alpha)
+    bgr = cv2.applyColorMap(u8, cv2.COLORMAP_JET)
+    return depth, bgr.reshape(depth.shape + (3,))

@@ -130,3 +130,22 @@ def test_high_disparity_full_size_properties(built_lib, H, W, D, B):
     # where one fp32 ulp of the output is already 9e-5 px and the two fp32 references differ by a few s32 steps).
     scale = cfg.max_disp / 192.0
     assert err.mean() <= EPE_BAR * scale and err.max() <= MAX_BAR * scale
+
+
+def test_gpu_depth_and_colormap_bit_exact(built_lib):
+    """ParseTensor (parser.cpp:79-118) on the GPU, bit-exact against cv2 for alpha = 11 and 9."""
+    cfg = arch.Config(64, 96, 3, 8)
+    rng = np.random.default_rng(5)
+    q = rng.integers(0, 400000, (2, 1, cfg.H, cfg.W), dtype=np.int64).astype(np.int32)
+    q[0, 0, 0, :8] = [0, 1, 2, 3, 1000, 2 ** 31 - 1, 383962, 7]          # inf, huge, saturating and ordinary depths
+    q[1, 0, 1, :4] = [5000, 50000, 500000, 5000000]
+    m = _model(cfg)
+    s8 = _s8(cfg, seed=77)
+    qn = m.infer(s8)                                                       # and a real network output
+    for alpha in (11.0, 9.0):
+        for arr in (q, qn):
+            depth, bgr = m.depth_color(arr, alpha)
+            d_ref, c_ref = pp.render_depth_colormap(arr[:, 0], alpha=alpha)
+            assert (depth.view(np.uint32) == d_ref.view(np.uint32)).all()      # bit-exact floats (inf included)
+            assert (bgr == c_ref).all()
+    m.close()

@@ -100,3 +100,25 @@ def test_golden_prepost_fixture():
     left, right = pp.split_side_by_side_nv12(g["frame"], 16, 48)
     assert (pp.cvt_nv12_to_tensor(left, right, 24, 16) == g["s8"]).all()
     assert (pp.cvt_nv12_to_tensor(left, right, 24, 16, correct_chroma=True) == g["s8_correct"]).all()
+
+
+def test_render_depth_colormap_semantics():
+    """parser.cpp:79-118: depth -> convertScaleAbs(alpha) -> JET, through cv2 itself; q = 0 (depth = inf) maps to bin 0."""
+    import cv2
+    q = np.array([[0, 1, 1000, 383962, 10 ** 6, 2 ** 31 - 1]], np.int32)
+    depth, bgr = pp.render_depth_colormap(q, alpha=11.0)
+    assert np.isinf(depth[0, 0]) and abs(depth[0, 3] - 0.3292) < 1e-3
+    lut = cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(1, -1), cv2.COLORMAP_JET)[0]
+    assert (bgr[0, 0] == lut[0]).all()                    # inf does not fit an int32: bin 0 on x86
+    assert (bgr[0, 3] == lut[4]).all()                    # 0.3292 m * 11 = 3.62 -> 4
+    assert (bgr[0, 1] == lut[255]).all() and (bgr[0, 2] == lut[255]).all()   # 1.26e5 m and 126 m saturate
+    assert (bgr[0, 5] == lut[0]).all()                                        # 5.9e-5 m * 11 rounds to 0
+
+
+def test_committed_jet_table_matches_cv2():
+    import cv2, os, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    txt = open(os.path.join(root, "hobot_stereonet_b200", "csrc", "jet_lut.inc")).read()
+    vals = np.array([int(v) for v in re.findall(r"\d+", txt.split("\n", 1)[1])], np.uint8).reshape(256, 3)
+    lut = cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(1, -1), cv2.COLORMAP_JET)[0]
+    assert (vals == lut).all()
