@@ -137,6 +137,7 @@ struct CsParams {        // k_conv_stream.cu: streaming convolution, one 32-chan
   int ncb_out, nbias;    // valid output channel blocks / biases of a slice (4 / 32 unless Cout < 32)
   int nco, ccs;          // output channels per unit (32, or 16 with one real channel), number of slices
   int XW, strips, nchunk, rpc, total_units, nxs;
+  int split;             // 1: main | corr accumulators per job (k_conv_stream SPLIT)
   int nslots, tmem_cols; // TMEM accumulator slots / allocated columns (5 / 512, or 2 / 256 in the two-CTAs-per-SM configuration)
   int ostride;           // 1, or 2: computed at stride 1, rows/columns with an odd index are not stored (C8 output only)
   int relu, res_mode;    // res_mode 0: C8 tensor like out (or none), 1: channel 0 of a C8 tensor, 2: fp32 plane

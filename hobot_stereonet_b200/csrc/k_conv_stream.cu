@@ -35,10 +35,14 @@ constexpr int CS_THREADS = 192;
 constexpr int CS_EPI_WARPS = 4;
 constexpr int CS_SLOTS = 5;                     // TMEM slots of the large configuration (the co-resident one uses 2)
 
-template <int NCO, bool PROF, int MINB>
+// SPLIT (NCO = 32, long jobs): two accumulators per job - `main` = hi*hi and `corr` = hi*lo + lo*hi - filled by
+// A_hi x [W_hi | W_lo] (N = 192) and A_lo x W_hi (N = 96).  The tensor core adds into TMEM with truncation, a bias that
+// grows with the chain length and the accumulator magnitude: keeping the small terms apart cuts it (config-3 shape EPE
+// 6.7e-4 -> see DESIGN.md §6) and the N = 192 MMA reads the A tile once for both halves.  Costs TMEM: 2 slots, not 5.
+template <int NCO, bool PROF, int MINB, bool SPLIT>
 __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams p) {
   constexpr int NCOL = 3 * NCO;                // accumulator columns of one job: [ky][NCO]
-  constexpr int SLOT_STRIDE = NCO == 32 ? 96 : 64;
+  constexpr int SLOT_STRIDE = SPLIT ? 192 : (NCO == 32 ? 96 : 64);
   extern __shared__ uint8_t smem_raw[];
   __shared__ float s_bias[32];
   __shared__ uint64_t bars[48];
@@ -125,7 +129,8 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
     // The tensor pipe queues only a few MMAs: uniform-datapath work between two MMA groups is exposed, so the loop
     // keeps ring positions as counters (no division) and builds descriptors with adds from hoisted bases.
     const bool leader = elect_one();
-    const uint32_t idesc = make_idesc_f16(128, NCOL);
+    const uint32_t idesc = make_idesc_f16(128, NCOL), idesc2 = make_idesc_f16(128, 2 * NCOL);
+    (void)idesc2;
     const uint32_t b_lbo = 2 * NCOL * 16;                   // bytes between the two K halves of a weight block
     const uint64_t dil16 = (uint64_t)d;
     const uint64_t a_desc0 = make_smem_desc(smem_u32(s_x), p.sub_bytes, 128);     // ring slot 0, hi plane
@@ -150,15 +155,24 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
             tc_fence_after();
             const uint64_t a_hi = a_desc0 + (uint64_t)slot * a_slot16, a_lo = a_hi + a_lo_off;
             if (leader) {
-              umma_f16(dcol, a_hi, w_hi, idesc, acc);
-              umma_f16_acc(dcol, a_hi, w_hi + NCOL, idesc);
-              umma_f16_acc(dcol, a_lo, w_hi, idesc);
-              umma_f16_acc(dcol, a_hi + dil16, w_hi + wkx16, idesc);
-              umma_f16_acc(dcol, a_hi + dil16, w_hi + wkx16 + NCOL, idesc);
-              umma_f16_acc(dcol, a_lo + dil16, w_hi + wkx16, idesc);
-              umma_f16_acc(dcol, a_hi + 2 * dil16, w_hi + 2 * wkx16, idesc);
-              umma_f16_acc(dcol, a_hi + 2 * dil16, w_hi + 2 * wkx16 + NCOL, idesc);
-              umma_f16_acc(dcol, a_lo + 2 * dil16, w_hi + 2 * wkx16, idesc);
+              if constexpr (SPLIT) {
+                umma_f16(dcol, a_hi, w_hi, idesc2, acc);                       // [main | corr] (+)= A_hi x [W_hi | W_lo]
+                umma_f16_acc(dcol + NCOL, a_lo, w_hi, idesc);                  // corr += A_lo x W_hi
+                umma_f16_acc(dcol, a_hi + dil16, w_hi + wkx16, idesc2);
+                umma_f16_acc(dcol + NCOL, a_lo + dil16, w_hi + wkx16, idesc);
+                umma_f16_acc(dcol, a_hi + 2 * dil16, w_hi + 2 * wkx16, idesc2);
+                umma_f16_acc(dcol + NCOL, a_lo + 2 * dil16, w_hi + 2 * wkx16, idesc);
+              } else {
+                umma_f16(dcol, a_hi, w_hi, idesc, acc);
+                umma_f16_acc(dcol, a_hi, w_hi + NCOL, idesc);
+                umma_f16_acc(dcol, a_lo, w_hi, idesc);
+                umma_f16_acc(dcol, a_hi + dil16, w_hi + wkx16, idesc);
+                umma_f16_acc(dcol, a_hi + dil16, w_hi + wkx16 + NCOL, idesc);
+                umma_f16_acc(dcol, a_lo + dil16, w_hi + wkx16, idesc);
+                umma_f16_acc(dcol, a_hi + 2 * dil16, w_hi + 2 * wkx16, idesc);
+                umma_f16_acc(dcol, a_hi + 2 * dil16, w_hi + 2 * wkx16 + NCOL, idesc);
+                umma_f16_acc(dcol, a_lo + 2 * dil16, w_hi + 2 * wkx16, idesc);
+              }
               umma_commit(&x_empty[slot]);
             }
             __syncwarp();
@@ -228,6 +242,12 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
             float v0[16], v1[16], v2[16];
             const uint32_t col = lane_addr + ts_cur * SLOT_STRIDE + hf * 16;
             cs_ld3x16(col, col + 32, col + 64, v0, v1, v2);
+            if constexpr (SPLIT) {                                             // + the corr accumulator
+              float c0[16], c1[16], c2[16];
+              cs_ld3x16(col + NCOL, col + NCOL + 32, col + NCOL + 64, c0, c1, c2);
+#pragma unroll
+              for (int c = 0; c < 16; ++c) { v0[c] += c0[c]; v1[c] += c1[c]; v2[c] += c2[c]; }
+            }
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
               f[hf * 16 + c] = a0[hf * 16 + c] + v2[c];
@@ -361,29 +381,33 @@ cudaError_t conv_stream_plan(CsPlan* plan, const Tens& in, int cin, int cout, in
   p.nslots = 2; p.tmem_cols = 256;
   if (nxs < need) { nxs = ring(227L * 1024 - 2048); p.nslots = CS_SLOTS; p.tmem_cols = 512; }
   if (nxs < std::max(4, p.nk16 + 1)) return cudaErrorInvalidValue;
+  // long jobs: main | corr accumulators (better accuracy, faster N = 192 MMAs), two 192-column TMEM slots
+  static const bool split_ok = !getenv("SNB_STREAM_SPLIT") || atoi(getenv("SNB_STREAM_SPLIT"));
+  p.split = (split_ok && p.nco == 32 && p.nk16 * kz >= 4 && p.tmem_cols == 512) ? 1 : 0;
+  if (p.split) p.nslots = 2;
   p.nxs = nxs;
   plan->smem = 128 + (size_t)p.w_bytes + (size_t)nxs * p.slot_bytes;
   return cudaSuccess;
 }
 
-template <int NCO, int MINB>
+template <int NCO, int MINB, bool SPLIT>
 static cudaError_t cs_launch_t(CsParams p, int grid, size_t smem, cudaStream_t st) {
   static bool attr_done[32] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 31]) {
-    cudaFuncSetAttribute(k_conv_stream<NCO, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
-    cudaFuncSetAttribute(k_conv_stream<NCO, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    cudaFuncSetAttribute(k_conv_stream<NCO, false, MINB, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    cudaFuncSetAttribute(k_conv_stream<NCO, true, MINB, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
     attr_done[dev & 31] = true;
   }
   static const int prof = getenv("SNB_TC_PROF") ? atoi(getenv("SNB_TC_PROF")) : 0;
-  if (!prof) return launch_k(k_conv_stream<NCO, false, MINB>, grid, CS_THREADS, smem, st, p);
+  if (!prof) return launch_k(k_conv_stream<NCO, false, MINB, SPLIT>, grid, CS_THREADS, smem, st, p);
   // diagnostics only: per-role cycle counters, synchronous read-back, max over CTAs
   static long long* d_prof = nullptr;
   if (!d_prof) cudaMalloc(&d_prof, 256 * 24 * sizeof(long long));
   p.prof = d_prof;
   cudaMemsetAsync(d_prof, 0, 256 * 24 * sizeof(long long), st);
-  cudaError_t e = launch_k(k_conv_stream<NCO, true, MINB>, grid, CS_THREADS, smem, st, p);
+  cudaError_t e = launch_k(k_conv_stream<NCO, true, MINB, SPLIT>, grid, CS_THREADS, smem, st, p);
   cudaStreamSynchronize(st);
   std::vector<long long> h(grid * 24);
   cudaMemcpy(h.data(), d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -416,8 +440,9 @@ cudaError_t launch_conv_stream(const CsPlan& plan, int N, const void* w, const f
   p.total_units = (int)(columns * p.nchunk);
   const int grid = p.total_units < plan.num_sms ? p.total_units : plan.num_sms;
   cudaError_t e;
-  if (p.nslots == 2) e = p.nco == 32 ? cs_launch_t<32, 2>(p, grid, plan.smem, st) : cs_launch_t<16, 2>(p, grid, plan.smem, st);
-  else e = p.nco == 32 ? cs_launch_t<32, 1>(p, grid, plan.smem, st) : cs_launch_t<16, 1>(p, grid, plan.smem, st);
+  if (p.split) e = cs_launch_t<32, 1, true>(p, grid, plan.smem, st);
+  else if (p.nslots == 2) e = p.nco == 32 ? cs_launch_t<32, 2, false>(p, grid, plan.smem, st) : cs_launch_t<16, 2, false>(p, grid, plan.smem, st);
+  else e = p.nco == 32 ? cs_launch_t<32, 1, false>(p, grid, plan.smem, st) : cs_launch_t<16, 1, false>(p, grid, plan.smem, st);
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
