@@ -442,12 +442,12 @@ cudaError_t launch_resblock_tc(const RbPlan& plan, int N, const void* wa, const 
                                cudaStream_t st) {
   RbParams p = plan.p;
   p.N = N; p.wa = static_cast<const __half*>(wa); p.wb = static_cast<const __half*>(wb); p.ba = ba; p.bb = bb;
-  // row chunks: about one unit per SM; every unit pays 4 halo rows, so never chop below 4 rows when avoidable
+  // row chunks: about one unit per SM (every unit pays 4 halo rows, but an idle SM pays more), at least 2 rows each
   const int rc_max = cdiv(p.H, p.dil);
   const int columns = N * p.strips * p.dil;                 // independent column walks
   int nchunk = plan.num_sms / columns;                      // floor: never spill a few units into a second wave
   if (nchunk < 1) nchunk = 1;
-  if (nchunk > cdiv(rc_max, 4)) nchunk = cdiv(rc_max, 4);
+  if (nchunk > cdiv(rc_max, 2)) nchunk = cdiv(rc_max, 2);
   p.rpc = cdiv(rc_max, nchunk);
   p.nchunk = cdiv(rc_max, p.rpc);
   p.total_units = columns * p.nchunk;
