@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
   if (warp == 0) {
     // ================================ bulk-copy producer ================================
     const __half* in = static_cast<const __half*>(p.in.p);
-    uint32_t it = 0, nw = 0, slot = 0, xpar = 1;
+    uint32_t it = 0, nw = 0;
     int cur_cc = -1;
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
       const CsUnit un = cs_decode(p, u);
@@ -101,27 +101,34 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
         }
         cur_cc = un.cc; ++nw;
       }
-      for (int j = 0; j < un.nr + 2; ++j) {
-        const int row = min(un.c + d * (un.i0 - 1 + j), p.H + p.in_pad - 1);
-        for (int dz = 0; dz < p.kz; ++dz) {
+      // A ring entry costs this warp ~700 cycles when issued one at a time (mbarrier poll, expect_tx, four bulk copies) -
+      // more than the ~450 cycles its MMAs take (profiles/: wait_x was a third of the issuer's time).  So the warp works
+      // on G entries at once: lane group g = lane / 4 takes entry e0 + g, its first lane polls that entry's slot and arms
+      // the barrier, its four lanes issue the (plane, chunk) copies.
+      const int dz0 = un.d - zpad < 0 ? zpad - un.d : 0, dz1 = un.d + p.kz - 1 - zpad >= p.D ? p.D - 1 - un.d + zpad : p.kz - 1;
+      const int EJ = (dz1 - dz0 + 1) * p.nk16, E = (un.nr + 2) * EJ;      // entries per job, per unit
+      const int G = min(8, max(1, p.nxs / 2));
+      const int g = lane >> 2, q4 = lane & 3;
+      for (int e0 = 0; e0 < E; e0 += G) {
+        const int e = e0 + g;
+        const bool act = g < G && e < E;
+        if (act) {
+          const uint32_t ge = it + (uint32_t)e, slot = ge % (uint32_t)p.nxs, par = ((ge / (uint32_t)p.nxs) & 1) ^ 1;
+          const int j = e / EJ, r = e - j * EJ, dz = dz0 + r / p.nk16, k16 = r % p.nk16;
+          const int row = min(un.c + d * (un.i0 - 1 + j), p.H + p.in_pad - 1);
           const int zin = un.d + dz - zpad;
-          if (zin < 0 || zin >= p.D) continue;
-          for (int k16 = 0; k16 < p.nk16; ++k16, ++it) {
-            if (lane == 0) {
-              CS_WAIT(tw1, &x_empty[slot], xpar);
-              mbar_expect_tx(&x_full[slot], 4 * p.sub_bytes);
-            }
-            __syncwarp();
-            if (lane < 4) {                                 // lane = plane*2 + chunk
-              const __half* src = in + (size_t)un.n * p.in.ss + (size_t)(lane >> 1) * p.in.lo +
-                                  ((size_t)(k16 * 2 + (lane & 1)) * p.D + zin) * p.in.slice +
-                                  ((ptrdiff_t)row * p.in.ws + (un.x0 - d)) * 8;
-              bulk_load(s_x + (size_t)slot * p.slot_bytes + (size_t)lane * p.sub_bytes, src, p.sub_bytes, &x_full[slot]);
-            }
-            if (++slot == (uint32_t)p.nxs) { slot = 0; xpar ^= 1; }
+          if (q4 == 0) {
+            CS_WAIT(tw1, &x_empty[slot], par);
+            mbar_expect_tx(&x_full[slot], 4 * p.sub_bytes);
           }
+          __syncwarp(0xfu << (g * 4));
+          const __half* src = in + (size_t)un.n * p.in.ss + (size_t)(q4 >> 1) * p.in.lo +      // q4 = plane*2 + chunk
+                              ((size_t)(k16 * 2 + (q4 & 1)) * p.D + zin) * p.in.slice + ((ptrdiff_t)row * p.in.ws + (un.x0 - d)) * 8;
+          bulk_load(s_x + (size_t)slot * p.slot_bytes + (size_t)q4 * p.sub_bytes, src, p.sub_bytes, &x_full[slot]);
         }
+        __syncwarp();
       }
+      it += (uint32_t)E;
     }
     if (PROF && lane == 0) { long long* q = p.prof + blockIdx.x * 24; q[0] = clock64() - t_start; q[1] = tw0; q[2] = tw1; q[3] = it; }
   } else if (warp == 1) {
