@@ -145,7 +145,7 @@ struct CsParams {        // k_conv_stream.cu: streaming convolution, one 32-chan
   long long* prof;       // SNB_TC_PROF=1: per-CTA cycle counters of the three roles
 };
 struct CsPlan { CsParams p; size_t smem; int num_sms; };
-struct CsLayer {         // k_conv_chain.cu: one convolution of a chain (device array)
+struct CsLayer {         // k_conv_pipe.cu: one convolution of a chain (device array)
   TV in, out, res;
   const __half* w; const float* bias;
   int relu, has_res;

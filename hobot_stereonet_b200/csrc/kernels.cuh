@@ -25,10 +25,10 @@ cudaError_t launch_conv_stream(const CsPlan& plan, int N, const void* w, const f
                                float* out_plane, const float* res_plane, int res_c8_ch0, int relu, int ostride, cudaStream_t st);
 void cs_pack_weights(const float* W, int cout, int cin, int kz, int ks, int NCO, std::vector<__half>& out);
 
-// k_conv_chain.cu — a chain of same-shape streaming convolutions in one persistent launch (M1: layer2)
-cudaError_t conv_chain_plan(CsPlan* plan, const Tens& in, int ch, int dil, int num_sms);
-bool conv_chain_units(CsPlan* plan, int N);
-cudaError_t launch_conv_chain(const CsPlan& plan, const CsLayer* d_layers, int nlayers, int* d_done, cudaStream_t st);
+// k_conv_pipe.cu — a chain of same-shape streaming convolutions as a layer pipeline in one launch (M1: layer2)
+cudaError_t conv_pipe_plan(CsPlan* plan, const Tens& in, int ch, int num_sms);
+int conv_pipe_layers_per_launch(const CsPlan& plan, int N, int nlayers);
+cudaError_t launch_conv_pipe(const CsPlan& plan, int N, const CsLayer* d_layers, int nlayers, int* d_done, cudaStream_t st);
 
 // k_mem.cu — HBM-bound kernels
 // P3 tail on device: s8 NCHW [B,6,H,W] -> C8 [2B][1][Hp][Wp][8] (x/128; left n<B, right n>=B; ch 3..7 = 0)

@@ -239,24 +239,28 @@ struct Builder {
     return out;
   }
 
-  // blocks [first, first + nblk) of `layer` (identity BasicBlocks on tensors of x's geometry) as one k_conv_chain launch
+  // blocks [first, first + nblk) of `layer` (identity BasicBlocks on tensors of x's geometry) as a layer pipeline
+  // (k_conv_pipe.cu): one CTA per (convolution, view, strip, channel slice), rows handed from layer to layer through L2
   bool chain(const std::string& layer, int first, int nblk, const Tens& x, int nmul, int dil, Tens* result) {
-    // opt-in: measured 12.2 us per layer2 convolution against ~10.5 us as separate launches in the CUDA graph (the
-    // dependency latency store -> fence -> flag -> acquire -> bulk copy replaces the launch latency, it does not remove it)
-    if (c->planes != 2 || !(c->cfg.flags & SNB_FLAG_CHAIN) || (c->cfg.flags & (SNB_FLAG_NO_TENSOR | SNB_FLAG_NO_STREAM | SNB_FLAG_KEEP_STAGES)) || nblk < 1) return false;
+    // opt-in: measured 434 us for layer2's 30 convolutions against ~295 us as separate launches (k_conv_pipe.cu header)
+    static const int env_pipe = getenv("SNB_PIPE") ? atoi(getenv("SNB_PIPE")) : -1;
+    const bool want = env_pipe >= 0 ? env_pipe != 0 : (c->cfg.flags & SNB_FLAG_PIPE) != 0;
+    if (c->planes != 2 || !want || (c->cfg.flags & (SNB_FLAG_NO_TENSOR | SNB_FLAG_NO_STREAM | SNB_FLAG_KEEP_STAGES)) || nblk < 1 || dil != 1) return false;
     CsPlan plan, splan;
-    if (conv_chain_plan(&plan, x, x.c, dil, c->num_sms) != cudaSuccess) return false;
+    if (conv_pipe_plan(&plan, x, x.c, c->num_sms) != cudaSuccess) return false;
     if (conv_stream_plan(&splan, x, x.c, x.c, dil, 1, c->num_sms) != cudaSuccess) return false;
-    { CsPlan probe = plan; if (!conv_chain_units(&probe, nmul * maxB)) return false; }
     std::vector<CsLayer> layers;
-    std::vector<Tens> outs;       // per layer: the output tensor (for the per-layer fallback)
+    std::vector<Tens> outs;       // per layer: its own output tensor (rows of several layers are in flight at once)
     Tens cur = x;
     double flops = 0, bytes = 0;
     for (int bi = first; bi < first + nblk; ++bi) {
       const std::string pb = layer + "." + std::to_string(bi);
       auto ia = c->convs.find(pb + ".conv_a"), ib = c->convs.find(pb + ".conv_b");
       if (ia == c->convs.end() || ib == c->convs.end() || ia->second.cin != x.c || ia->second.cout != x.c || ib->second.cin != x.c ||
-          ib->second.cout != x.c || ia->second.ks != 3 || ib->second.ks != 3 || ia->second.kz != 1) return false;
+          ib->second.cout != x.c || ia->second.ks != 3 || ib->second.ks != 3 || ia->second.kz != 1) {
+        for (const Tens& t : outs) free(t);
+        return false;
+      }
       Tens a = alloc(nmul, x.c, 1, x.h, x.w, x.pad), o = alloc(nmul, x.c, 1, x.h, x.w, x.pad);
       CsLayer la{}, lb{};
       la.in = view(cur); la.out = view(a); la.w = stream_weights(pb + ".conv_a", ia->second, 32); la.bias = ia->second.b; la.relu = 1;
@@ -268,25 +272,22 @@ struct Builder {
       const double px = (double)nmul * x.h * x.w;
       flops += 2 * 2.0 * px * x.c * x.c * 9;
       bytes += 4.0 * px * x.c * 5;
-      free(a);
-      if (bi > first) free(cur);
       cur = o;
     }
+    for (size_t i = 0; i + 1 < outs.size(); ++i) free(outs[i]);     // reusable by the ops AFTER this one
     CsLayer* d_layers = nullptr; int* d_done = nullptr;
-    if (cudaMalloc(&d_layers, layers.size() * sizeof(CsLayer)) != cudaSuccess || cudaMalloc(&d_done, 1024 * sizeof(int)) != cudaSuccess) { fail = true; return false; }
+    const size_t n_done = layers.size() * (size_t)c->num_sms;
+    if (cudaMalloc(&d_layers, layers.size() * sizeof(CsLayer)) != cudaSuccess || cudaMalloc(&d_done, n_done * sizeof(int)) != cudaSuccess) { fail = true; return false; }
     cudaMemcpy(d_layers, layers.data(), layers.size() * sizeof(CsLayer), cudaMemcpyHostToDevice);
     c->wallocs.push_back(d_layers); c->wallocs.push_back(d_done);
-    Op op; op.name = layer + "." + std::to_string(first) + "-" + std::to_string(first + nblk - 1) + " [tc-chain x" + std::to_string(layers.size()) + "]";
+    Op op; op.name = layer + "." + std::to_string(first) + "-" + std::to_string(first + nblk - 1) + " [tc-pipe x" + std::to_string(layers.size()) + "]";
     op.flops = flops; op.bytes = bytes;
     const int nl = (int)layers.size();
     const Tens xin = x;
     op.fn = [plan, splan, layers, outs, xin, d_layers, d_done, nl, nmul](int B, cudaStream_t st) {
-      CsPlan pl = plan;
-      if (conv_chain_units(&pl, nmul * B)) return launch_conv_chain(pl, d_layers, nl, d_done, st);
-      // more units than SMs (large batches): the same layers, one k_conv_stream launch each
+      if (conv_pipe_layers_per_launch(plan, nmul * B, nl) >= 2) return launch_conv_pipe(plan, nmul * B, d_layers, nl, d_done, st);
+      // too many units per layer for a pipeline (large batches): the same layers, one k_conv_stream launch each
       for (int l = 0; l < nl; ++l) {
-        const Tens& in_t = l == 0 ? xin : outs[l - 1];
-        (void)in_t;
         CsPlan sp = splan;
         sp.p.in = layers[l].in;
         Tens out_t = outs[l];

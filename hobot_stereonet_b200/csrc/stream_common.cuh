@@ -1,4 +1,4 @@
-// Helpers shared by the streaming tcgen05 convolution kernels (k_conv_stream.cu, k_conv_chain.cu).
+// Helpers shared by the streaming tcgen05 convolution kernels (k_conv_stream.cu, k_conv_pipe.cu).
 #pragma once
 #include "common.cuh"
 #include "tc_ptx.cuh"

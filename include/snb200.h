@@ -49,7 +49,7 @@ enum {
   SNB_FLAG_NO_TENSOR = 8,     /* diagnostics: SNB_PREC_TC_F16X2 storage, but every convolution on the CUDA-core kernel */
   SNB_FLAG_NO_FUSE = 16,      /* diagnostics: residual blocks as two separate convolution launches */
   SNB_FLAG_NO_STREAM = 32,    /* diagnostics: tiled k_conv_tc / CUDA-core kernels instead of the streaming convolution */
-  SNB_FLAG_CHAIN = 64         /* experiment: layer2's identity blocks as one persistent launch with neighbour sync (slower: DESIGN.md §6) */
+  SNB_FLAG_PIPE = 64          /* experiment: layer2's identity blocks as one layer-pipelined launch (k_conv_pipe.cu; correct but slower) */
 };
 
 /* Replaces dnn_node_para_ptr_->{model_file, model_task_type, task_num} (stereonet_node.cpp:136-144)
