@@ -97,6 +97,13 @@ struct ConvTo1Params {   // Cout = 1 convolutions (conv3d_alone, refinement conv
   int half;
 };
 
+struct ConvFirstParams { // k_conv_first (firstconv.0): Cin = 3, 3x3, stride 2, Cout = 32; weights in the constant bank
+  TV in, out;
+  int Ho, Wo, relu;
+  float w[27 * 32];      // [(ci*9 + ky*3 + kx)][co]
+  float b[32];
+};
+
 struct TcConvParams {    // k_conv_tc.cu
   TV in, out, res;       // split-fp16 tensors
   const __half* w; const float* bias;

@@ -9,8 +9,9 @@
 //                 M = 128 pixels, N = NCO output channels x 3 kernel rows, K = 16.  Row i of the input therefore
 //                 contributes to output rows i-1, i, i+1; the epilogue keeps two partial output rows in registers.
 //   NCO           32: C8 split-fp16 output (+ bias, optional residual, optional ReLU).
-//                 16: single-output-channel convolutions (channel 0 real, 1-15 zero weights: N must be a multiple
-//                     of 16 at M = 128) writing an fp32 plane (+ bias, optional residual, optional ReLU).
+//                 16: single-output-channel convolutions (N must be a multiple of 16 at M = 128: W_hi | W_lo | W_hi
+//                     for the lo plane sit in columns 0 | 1 | 2 of the group, 2 MMAs per tap instead of 3) writing an
+//                     fp32 plane (+ bias, optional residual, optional ReLU).
 //   stride 2      computed at stride 1, every other row / column stored (firstconv.0/.2, layer2.0): 4x the MMAs of a
 //                 true strided kernel but still 2-3x faster than the CUDA-core path these small layers used before.
 //   1x1           packed as the centre tap of a 3x3 (shortcut convolutions, lastconv.1).
@@ -169,6 +170,15 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
                 umma_f16_acc(dcol + NCOL, a_lo + dil16, w_hi + wkx16, idesc);
                 umma_f16_acc(dcol, a_hi + 2 * dil16, w_hi + 2 * wkx16, idesc2);
                 umma_f16_acc(dcol + NCOL, a_lo + 2 * dil16, w_hi + 2 * wkx16, idesc);
+              } else if constexpr (NCO == 16) {
+                // one real output channel: W_hi | W_lo share a 16-column group (columns 0, 1), the second weight block
+                // holds W_hi in column 2 for the lo plane: 2 MMAs per tap, hi*hi | hi*lo | lo*hi in columns 0 | 1 | 2
+                umma_f16(dcol, a_hi, w_hi, idesc, acc);
+                umma_f16_acc(dcol, a_lo, w_hi + NCOL, idesc);
+                umma_f16_acc(dcol, a_hi + dil16, w_hi + wkx16, idesc);
+                umma_f16_acc(dcol, a_lo + dil16, w_hi + wkx16 + NCOL, idesc);
+                umma_f16_acc(dcol, a_hi + 2 * dil16, w_hi + 2 * wkx16, idesc);
+                umma_f16_acc(dcol, a_lo + 2 * dil16, w_hi + 2 * wkx16 + NCOL, idesc);
               } else {
                 umma_f16(dcol, a_hi, w_hi, idesc, acc);
                 umma_f16_acc(dcol, a_hi, w_hi + NCOL, idesc);
@@ -318,12 +328,12 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
           if (lane == 0) mbar_arrive(&s_empty[ts]);
           if (++ts == (uint32_t)p.nslots) { ts = 0; fpar ^= 1; }
           if (ok) {
-            float f = a0 + v2[0] + r;
+            float f = a0 + (v2[0] + (v2[1] + v2[2])) + r;   // hi*hi + (hi*lo + lo*hi)
             if (p.relu) f = fmaxf(f, 0.f);
             p.out_plane[o] = f;
           }
-          a0 = a1 + v1[0];
-          a1 = v0[0] + bias;
+          a0 = a1 + (v1[0] + (v1[1] + v1[2]));
+          a1 = (v0[0] + (v0[1] + v0[2])) + bias;
         }
       }
     }
@@ -353,6 +363,12 @@ void cs_pack_weights(const float* W, int cout, int cin, int kz, int ks, int NCO,
             const int cc = NCO == 32 ? co / 32 : 0, cl = NCO == 32 ? co % 32 : co;
             const int k16 = ci / 16, half = (ci % 16) / 8, e = ci % 8;
             const size_t blk = ((((size_t)cc * nk16 + k16) * kz + dz) * 3 + kx) * 2 + half;
+            if (NCO == 16) {     // one output channel: block 1 = [W_hi, W_lo, 0...] (x A_hi), block 2 = [0, 0, W_hi, 0...] (x A_lo)
+              out[(blk * 2 * ncol + ky * NCO + 0) * 8 + e] = hi;
+              out[(blk * 2 * ncol + ky * NCO + 1) * 8 + e] = lo;
+              out[(blk * 2 * ncol + ncol + ky * NCO + 2) * 8 + e] = hi;
+              continue;
+            }
             out[(blk * 2 * ncol + ky * NCO + cl) * 8 + e] = hi;
             out[(blk * 2 * ncol + ncol + ky * NCO + cl) * 8 + e] = lo;
           }

@@ -15,6 +15,15 @@ template <> struct St<float> {
     const float4 a = __ldg(p), b = __ldg(p + 1);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   }
+  struct Raw { float4 a, b; };                               // an 8-channel block as loaded, before conversion
+  __device__ __forceinline__ static Raw ldraw(const void* base, size_t idx, size_t) {
+    const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(base) + idx);
+    Raw r; r.a = __ldg(p); r.b = __ldg(p + 1);
+    return r;
+  }
+  __device__ __forceinline__ static void cvt(const Raw& r, float (&v)[8]) {
+    v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+  }
   __device__ __forceinline__ static void st8(void* base, size_t idx, size_t, const float (&v)[8]) {
     float4* p = reinterpret_cast<float4*>(static_cast<float*>(base) + idx);
     p[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -33,6 +42,21 @@ template <> struct St<__half> {
     const uint4 l = __ldg(reinterpret_cast<const uint4*>(p + lo_off));
     const __half2* h2 = reinterpret_cast<const __half2*>(&h);
     const __half2* l2 = reinterpret_cast<const __half2*>(&l);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = __half22float2(h2[j]), b = __half22float2(l2[j]);
+      v[2 * j] = a.x + b.x; v[2 * j + 1] = a.y + b.y;
+    }
+  }
+  struct Raw { uint4 h, l; };
+  __device__ __forceinline__ static Raw ldraw(const void* base, size_t idx, size_t lo_off) {
+    const __half* p = static_cast<const __half*>(base) + idx;
+    Raw r; r.h = __ldg(reinterpret_cast<const uint4*>(p)); r.l = __ldg(reinterpret_cast<const uint4*>(p + lo_off));
+    return r;
+  }
+  __device__ __forceinline__ static void cvt(const Raw& r, float (&v)[8]) {
+    const __half2* h2 = reinterpret_cast<const __half2*>(&r.h);
+    const __half2* l2 = reinterpret_cast<const __half2*>(&r.l);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 a = __half22float2(h2[j]), b = __half22float2(l2[j]);

@@ -49,6 +49,7 @@ enum {
   SNB_FLAG_NO_TENSOR = 8,     /* diagnostics: SNB_PREC_TC_F16X2 storage, but every convolution on the CUDA-core kernel */
   SNB_FLAG_NO_FUSE = 16,      /* diagnostics: residual blocks as two separate convolution launches */
   SNB_FLAG_NO_STREAM = 32,    /* diagnostics: tiled k_conv_tc / CUDA-core kernels instead of the streaming convolution */
+  SNB_FLAG_NO_HBMCONV = 128,  /* diagnostics: firstconv.0 on the tcgen05 streaming kernel instead of k_conv_first (k_conv_hbm.cu) */
   SNB_FLAG_PIPE = 64          /* experiment: layer2's identity blocks as one layer-pipelined launch (k_conv_pipe.cu; correct but slower) */
 };
 
