@@ -27,6 +27,26 @@ def test_cli_missing_model_fails_like_reference(built_lib):
     assert "sub_hbmem_topic_name: hbmem_stereo_img" in r.stderr and "ros_img_topic_name: /stereonet_node_output" in r.stderr
 
 
+def test_ros2_shell_compiles_and_links_against_stub_rclcpp(built_lib, tmp_path):
+    """SURVEY.md §8f rank 2: the ROS 2 shell (hobot_stereonet_b200/ros2) cannot be built here (no rclcpp in the image);
+    it is compiled and LINKED against minimal stand-in headers (tests/ros_stubs) with the real host library, so the calls it
+    makes into StereonetNode and the message fields it forwards (stereonet_node.cpp:27-35,108-118,657,1064) stay in sync."""
+    src = os.path.join(ROOT, "hobot_stereonet_b200", "ros2", "src", "stereonet_ros_node.cpp")
+    lib = os.path.join(ROOT, "hobot_stereonet_b200", "lib")
+    exe = str(tmp_path / "ros_shell")
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "tests", "ros_stubs"),
+                        "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "hobot_stereonet_b200", "host"), src, "-o", exe,
+                        "-L" + lib, "-lstereonet_host", "-lsnb200", "-Wl,-rpath," + lib, "-lpthread"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # the default model_file does not exist here: the shell must fail like the reference node (log + shutdown), not crash
+    r = subprocess.run([exe], capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0 and "Node init fail!" in r.stderr
+    # same package / executable names and launch arguments as the reference (hobot_stereonet.launch.py:35-49)
+    launch = open(os.path.join(ROOT, "hobot_stereonet_b200", "ros2", "launch", "hobot_stereonet.launch.py")).read()
+    for needle in ('package="hobot_stereonet"', 'executable="hobot_stereonet"', '"config_file"', '"model_file"'):
+        assert needle in launch
+
+
 def test_sys_alloc_roundtrip(built_lib):
     p = C.c_void_p()
     assert built_lib.snb_sys_alloc(C.byref(p), 4096) == 0 and p.value and p.value % 64 == 0
