@@ -304,20 +304,37 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
           }
         }
       } else {
-        // single output channel: columns [ky*16 + 0]; fp32 plane out [n][D][H][W], optional residual
+        // single output channel: columns [ky*16 + 0..2]; fp32 plane out [n][D][H][W], optional residual
         float a0 = 0.f, a1 = 0.f;
         const float bias = s_bias[0];
+        // The residual of a row is one cold global load: issued just before the wait on the row's accumulator its latency
+        // was the epilogue's whole period (1.8 k cycles per job against ~0.5 k of MMAs at full resolution), so the loads
+        // run RES_AHEAD jobs ahead of their use.
+        constexpr int RES_AHEAD = 3;
+        struct ResRaw { unsigned short h, l; float f; };    // kept as loaded: converting would wait for the load
+        ResRaw rq[RES_AHEAD];
+        auto res_load = [&](int j) -> ResRaw {
+          ResRaw q; q.h = 0; q.l = 0; q.f = 0.f;
+          const int row = un.c + d * (un.i0 - 2 + j);
+          if (!(col_ok && j >= 2 && j < un.nr + 2 && row < p.H)) return q;
+          if (p.res_mode == 1) {                            // channel 0 of a C8 split-fp16 tensor
+            const unsigned short* rp = reinterpret_cast<const unsigned short*>(p.res.p) + (size_t)un.n * p.res.ss + ((size_t)row * p.res.ws + opx) * 8;
+            q.h = __ldg(rp); q.l = __ldg(rp + p.res.lo);
+          } else if (p.res_mode == 2) {
+            q.f = __ldg(p.res_plane + (((size_t)un.n * p.D + un.d) * p.H + row) * p.W + opx);
+          }
+          return q;
+        };
+#pragma unroll
+        for (int k = 0; k < RES_AHEAD; ++k) rq[k] = res_load(k);
         for (int j = 0; j < un.nr + 2; ++j) {
           const int row = un.c + d * (un.i0 - 2 + j);
           const bool ok = col_ok && j >= 2 && row < p.H;
-          float r = 0.f;
           const size_t o = (((size_t)un.n * p.D + un.d) * p.H + (ok ? row : 0)) * p.W + (ok ? opx : 0);
-          if (ok && p.res_mode == 1) {                      // channel 0 of a C8 split-fp16 tensor
-            const __half* rp = static_cast<const __half*>(p.res.p) + (size_t)un.n * p.res.ss + ((size_t)row * p.res.ws + opx) * 8;
-            r = __half2float(__ldg(rp)) + __half2float(__ldg(rp + p.res.lo));
-          } else if (ok && p.res_mode == 2) {
-            r = __ldg(p.res_plane + o);
-          }
+          const ResRaw rr = rq[0];
+#pragma unroll
+          for (int k = 0; k + 1 < RES_AHEAD; ++k) rq[k] = rq[k + 1];
+          rq[RES_AHEAD - 1] = res_load(j + RES_AHEAD);
           CS_WAIT(tw0, &s_full[ts], fpar);
           tc_fence_after();
           float v0[16], v1[16], v2[16];
@@ -328,6 +345,7 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
           if (lane == 0) mbar_arrive(&s_empty[ts]);
           if (++ts == (uint32_t)p.nslots) { ts = 0; fpar ^= 1; }
           if (ok) {
+            const float r = rr.f + (__half2float(__ushort_as_half(rr.h)) + __half2float(__ushort_as_half(rr.l)));
             float f = a0 + (v2[0] + (v2[1] + v2[2])) + r;   // hi*hi + (hi*lo + lo*hi)
             if (p.relu) f = fmaxf(f, 0.f);
             p.out_plane[o] = f;
