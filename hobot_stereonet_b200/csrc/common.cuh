@@ -97,10 +97,10 @@ struct ConvTo1Params {   // Cout = 1 convolutions (conv3d_alone, refinement conv
   int half;
 };
 
-struct ConvFirstParams { // k_conv_first (firstconv.0): Cin = 3, 3x3, stride 2, Cout = 32; weights in the constant bank
+struct ConvFirstParams { // k_conv_first: Cin = 3 stride 2 (firstconv.0) or Cin = 4 stride 1 (refinement conv_in), 3x3, Cout = 32
   TV in, out;
-  int Ho, Wo, relu;
-  float w[27 * 32];      // [(ci*9 + ky*3 + kx)][co]
+  int Ho, Wo, relu, cin, stride;
+  float w[36 * 32];      // [(ci*9 + ky*3 + kx)][co]: rides in the kernel parameters = the constant bank
   float b[32];
 };
 

@@ -30,9 +30,9 @@ cudaError_t conv_pipe_plan(CsPlan* plan, const Tens& in, int ch, int num_sms);
 int conv_pipe_layers_per_launch(const CsPlan& plan, int N, int nlayers);
 cudaError_t launch_conv_pipe(const CsPlan& plan, int N, const CsLayer* d_layers, int nlayers, int* d_done, cudaStream_t st);
 
-// k_conv_hbm.cu — firstconv.0 of the tensor path (Cin = 3, stride 2): CUDA cores, weights in the constant bank
-void conv_first_pack(const float* W, const float* bias, ConvFirstParams* p);
-cudaError_t launch_conv_first(const ConvFirstParams& p, int N, bool half, cudaStream_t st);
+// k_conv_hbm.cu — few-input-channel convolutions of the tensor path (firstconv.0, refinement conv_in): CUDA cores, weights in the constant bank
+void conv_first_pack(const float* W, const float* bias, int cin, ConvFirstParams* p);
+cudaError_t launch_conv_first(const ConvFirstParams& p, int N, cudaStream_t st);
 
 // k_mem.cu — HBM-bound kernels
 // P3 tail on device: s8 NCHW [B,6,H,W] -> C8 [2B][1][Hp][Wp][8] (x/128; left n<B, right n>=B; ch 3..7 = 0)

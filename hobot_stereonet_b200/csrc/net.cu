@@ -315,15 +315,16 @@ struct Builder {
     const double px = (double)nmul * in.d * ho * wo;
     op.flops = 2.0 * px * cw.cout * cw.cin * cw.ks * cw.ks * cw.kz;
     op.bytes = 4.0 * (nmul * (double)in.d * in.h * in.w * in.cb * 8 + px * out.cb * 8 * (res ? 2 : 1));
-    if (c->planes == 2 && !(c->cfg.flags & SNB_FLAG_NO_HBMCONV) && cw.cin == 3 && cw.cout == 32 && stride == 2 && cw.ks == 3 && cw.kz == 1 &&
-        in.d == 1 && in.pad >= 1 && !res) {
-      // the 3-channel image convolution: 13 FLOP per byte moved, CUDA cores with the weights in the constant bank
+    if (c->planes == 2 && !(c->cfg.flags & SNB_FLAG_NO_HBMCONV) && cw.cout == 32 && cw.ks == 3 && cw.kz == 1 && in.d == 1 && in.pad >= 1 && !res &&
+        dil == 1 && cw.cin == 3 && stride == 2) {
+      // the 3-channel image convolution: 13 FLOP per byte moved, CUDA cores with the weights in the constant bank (k_conv_hbm.cu);
+      // the 4-channel refinement conv_in measured 38.6 us this way against 40.0 us on k_conv_tc (FMA bound) and stays there
       ConvFirstParams fp{};
-      fp.in = view(in); fp.out = view(out); fp.Ho = ho; fp.Wo = wo; fp.relu = relu ? 1 : 0;
-      conv_first_pack(c->wts[name + ".weight"].data.data(), c->wts[name + ".bias"].data.data(), &fp);
-      op.fn = [fp, nmul](int B, cudaStream_t st) { return launch_conv_first(fp, nmul * B, true, st); };
+      fp.in = view(in); fp.out = view(out); fp.Ho = ho; fp.Wo = wo; fp.relu = relu ? 1 : 0; fp.stride = stride;
+      conv_first_pack(c->wts[name + ".weight"].data.data(), c->wts[name + ".bias"].data.data(), cw.cin, &fp);
+      op.fn = [fp, nmul](int B, cudaStream_t st) { return launch_conv_first(fp, nmul * B, st); };
       op.name += " [hbm]";
-      op.bytes = 2.0 * nmul * (double)in.h * in.w * 8 + 4.0 * px * out.cb * 8;   // hi plane of one channel block in, C8 split out
+      op.bytes = (cw.cin == 3 ? 2.0 : 4.0) * nmul * (double)in.h * in.w * 8 + 4.0 * px * out.cb * 8;   // one channel block in, C8 split out
       c->ops.push_back(op);
       return out;
     }
