@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsnb200.so")
 
 SNB_OK, SNB_ERR_INVALID, SNB_ERR_MODEL, SNB_ERR_CUDA, SNB_ERR_NOMEM, SNB_ERR_BUSY = 0, -1, -2, -3, -4, -5
 PREC_FP32, PREC_TC_F16X2 = 0, 1
-FLAG_KEEP_STAGES, FLAG_NO_GRAPH, FLAG_CORRECT_CHROMA, FLAG_NO_TENSOR, FLAG_NO_FUSE, FLAG_NO_STREAM, FLAG_PIPE, FLAG_NO_HBMCONV = 1, 2, 4, 8, 16, 32, 64, 128
+FLAG_KEEP_STAGES, FLAG_NO_GRAPH, FLAG_CORRECT_CHROMA, FLAG_NO_TENSOR, FLAG_NO_FUSE, FLAG_NO_STREAM, FLAG_PIPE, FLAG_NO_HBMCONV, FLAG_NO_COALESCE = 1, 2, 4, 8, 16, 32, 64, 128, 256
 LAYOUT_NCHW, TENSOR_S8, TENSOR_S32 = 2, 1, 3
 
 
@@ -65,6 +65,7 @@ def load() -> C.CDLL:
         "snb_infer_device": (C.c_int, [vp, vp, vp, i32, vp]),
         "snb_infer_nv12": (C.c_int, [vp, vp, vp, i32]),
         "snb_get_rt_stat": (C.c_int, [vp, C.POINTER(SnbRtStat)]),
+        "snb_get_pass_count": (i64, [vp]),
         "snb_last_error": (C.c_char_p, [vp]),
         "snb_version": (C.c_char_p, []),
         "snb_debug_read": (i64, [vp, C.c_char_p, vp, u64, C.POINTER(i32 * 5)]),
@@ -200,6 +201,9 @@ class Model:
 
     def wait_all(self):
         self._check(self._l.snb_wait_all(self._h))
+
+    def pass_count(self) -> int:
+        return int(self._l.snb_get_pass_count(self._h))
 
     def rt_stat(self) -> SnbRtStat:
         s = SnbRtStat()

@@ -232,6 +232,7 @@ static int run_chunk(snb_ctx* c, int B, const int8_t* d_in, const uint8_t* d_fra
   e = launch_post_quant(d, d_out, c->H, c->W, c->qmul, st);
   if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "post: %s", cudaGetErrorString(e)); return SNB_ERR_CUDA; }
   c->last_B = B;
+  ++c->n_passes;
   return SNB_OK;
 }
 
@@ -311,6 +312,8 @@ int snb_wait_all(snb_ctx* c) {
   c->cv_push.wait(lk, [&] { return c->inflight == 0 || c->stop; });
   return SNB_OK;
 }
+
+int64_t snb_get_pass_count(const snb_ctx* c) { return c ? (int64_t)c->n_passes : SNB_ERR_INVALID; }
 
 int snb_get_rt_stat(const snb_ctx* c, snb_rt_stat* s) {
   if (!c || !s) return SNB_ERR_INVALID;
@@ -441,7 +444,7 @@ int snb_profile_pass(snb_ctx* c, int32_t batch, snb_kernel_time* out, int32_t ca
 
 }  // extern "C"
 
-// Retire the oldest in-flight call: wait for its device->host copy, fire the callback, free its task slot.
+// Retire the oldest in-flight pass: wait for its device->host copies, fire the callbacks, free its task slots.
 static void retire_oldest(snb_ctx* c) {
   AsyncSlot& sl = c->slots[c->n_ret % c->slots.size()];
   int status = SNB_OK;
@@ -458,7 +461,7 @@ static void retire_oldest(snb_ctx* c) {
     c->stat.gpu_ms = ms;
     c->stat.infer_time_ms = (int)((t1 - sl.t0) * 1e3 + 0.5);
     c->stat.kernel_launches = (int)c->ops.size() + 2;
-    c->fps_in += sl.task.batch; c->fps_out += sl.task.batch;
+    c->fps_in += sl.batch; c->fps_out += sl.batch;
     c->stat.fps_updated = 0;
     if (t1 - c->fps_t0 >= 1.0) {
       c->stat.input_fps = (float)(c->fps_in / (t1 - c->fps_t0));
@@ -467,62 +470,109 @@ static void retire_oldest(snb_ctx* c) {
     }
     st = c->stat;
   }
-  if (sl.task.done) sl.task.done(sl.task.user, status, &st);
+  for (const Task& t : sl.tasks)
+    if (t.done) t.done(t.user, status, &st);
+  const int n = (int)sl.tasks.size();
+  sl.tasks.clear();
   sl.busy = false;
   ++c->n_ret;
   {
     std::unique_lock<std::mutex> lk(c->mu);
-    --c->inflight;
+    c->inflight -= n;
   }
   c->cv_push.notify_all();
 }
 
-// Enqueue one call (batch <= max_batch) without waiting for it: H2D on st_in, kernels on the compute stream,
-// D2H on st_out, chained by events.
-static int enqueue_async(snb_ctx* c, const Task& t) {
+// Enqueue one pass (sum of the calls' batches <= max_batch) without waiting for it: H2D on st_in, kernels on the compute
+// stream, D2H on st_out, chained by events.
+static int enqueue_async(snb_ctx* c, const std::vector<Task>& group) {
   AsyncSlot& sl = c->slots[c->n_enq % c->slots.size()];
   std::lock_guard<std::mutex> run(c->run_mu);
   CK(c, cudaSetDevice(c->cfg.device));
-  sl.task = t; sl.t0 = now_s();
-  CK(c, cudaMemcpyAsync(sl.d_in, t.in, c->in_bytes * t.batch, cudaMemcpyHostToDevice, c->st_in));
+  sl.tasks = group; sl.t0 = now_s();
+  int B = 0;
+  for (const Task& t : group) {
+    CK(c, cudaMemcpyAsync(sl.d_in + (size_t)B * c->in_bytes, t.in, c->in_bytes * t.batch, cudaMemcpyHostToDevice, c->st_in));
+    B += t.batch;
+  }
+  sl.batch = B;
   CK(c, cudaEventRecord(sl.e_in, c->st_in));
   CK(c, cudaStreamWaitEvent(c->stream, sl.e_in, 0));
-  int r = run_chunk(c, t.batch, sl.d_in, nullptr, sl.d_out, c->stream);
+  int r = run_chunk(c, B, sl.d_in, nullptr, sl.d_out, c->stream);
   if (r != SNB_OK) return r;
   CK(c, cudaEventRecord(sl.e_done, c->stream));
   CK(c, cudaStreamWaitEvent(c->st_out, sl.e_done, 0));
-  CK(c, cudaMemcpyAsync(t.out, sl.d_out, c->out_bytes * t.batch, cudaMemcpyDeviceToHost, c->st_out));
+  B = 0;
+  for (const Task& t : group) {
+    CK(c, cudaMemcpyAsync(t.out, sl.d_out + (size_t)B * c->H * c->W, c->out_bytes * t.batch, cudaMemcpyDeviceToHost, c->st_out));
+    B += t.batch;
+  }
   CK(c, cudaEventRecord(sl.e_out, c->st_out));
   sl.busy = true;
   ++c->n_enq;
   return SNB_OK;
 }
 
+// The worker thread (= the reference's PostProcess thread: callbacks fire here).
+// Coalescing (max_batch > 1, not SNB_FLAG_NO_COALESCE): at configs[1] one pair per pass leaves the GPU latency-bound
+// (1.58 ms), two pairs per pass cost 2.68 ms and three 3.81 ms (tools/batch_probe.py), so queued calls are merged into
+// one pass of up to max_batch pairs.  To let calls queue up the worker keeps only TWO passes on the GPU (one running,
+// one behind it - enough to hide copies and launch latency) and, while a pass is still running, gives the caller a
+// moment (200 us) to submit the rest of a batch before it launches the next pass.  Per-call semantics do not change:
+// own input / output buffers, own callback, callbacks in submission order.
 static void worker_main(snb_ctx* c) {
+  const bool coalesce = c->maxB > 1 && !(c->cfg.flags & SNB_FLAG_NO_COALESCE);
+  const uint64_t max_passes = coalesce ? std::min<uint64_t>(2, c->slots.size()) : c->slots.size();
+  const int cap = std::max(1, c->cfg.task_num);
   for (;;) {
-    Task t{};
-    bool have = false;
+    std::vector<Task> group;
     {
       std::unique_lock<std::mutex> lk(c->mu);
-      if (c->n_enq == c->n_ret) c->cv_pop.wait(lk, [&] { return c->stop || !c->queue.empty(); });
-      if (!c->queue.empty()) { t = c->queue.front(); c->queue.pop_front(); have = true; }
-      else if (c->n_enq == c->n_ret) return;   // stop requested, nothing queued, nothing in flight
+      if (c->queue.empty()) {
+        if (c->n_enq == c->n_ret) {
+          c->cv_pop.wait(lk, [&] { return c->stop || !c->queue.empty(); });
+          if (c->queue.empty()) return;          // stop requested, nothing queued, nothing in flight
+        } else if (coalesce) {
+          // passes in flight and nothing queued: sleep until a call arrives, but keep an eye on the oldest pass
+          c->cv_pop.wait_for(lk, std::chrono::microseconds(50), [&] { return c->stop || !c->queue.empty(); });
+        }
+      }
+      if (!c->queue.empty()) { group.push_back(c->queue.front()); c->queue.pop_front(); }
     }
-    if (!have) { retire_oldest(c); continue; }  // queue drained: finish what is in flight
-    if (c->n_enq - c->n_ret == c->slots.size()) retire_oldest(c);
+    if (group.empty()) {
+      if (c->n_enq == c->n_ret) continue;
+      if (!coalesce || c->stop || cudaEventQuery(c->slots[c->n_ret % c->slots.size()].e_out) != cudaErrorNotReady) retire_oldest(c);
+      continue;
+    }
+    while (c->n_enq - c->n_ret >= max_passes) retire_oldest(c);
+    int total = group[0].batch;
     int r;
-    if (t.batch <= c->maxB) {
-      r = enqueue_async(c, t);
+    if (total <= c->maxB) {
+      if (coalesce) {
+        const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(200);
+        std::unique_lock<std::mutex> lk(c->mu);
+        for (;;) {
+          while (!c->queue.empty() && total + c->queue.front().batch <= c->maxB) {
+            group.push_back(c->queue.front()); total += c->queue.front().batch; c->queue.pop_front();
+          }
+          // stop gathering: the pass is full, the next call does not fit, the caller cannot submit more (every task
+          // slot is taken), or the GPU has nothing left to do
+          if (total >= c->maxB || !c->queue.empty() || c->inflight >= cap || c->n_enq == c->n_ret || c->stop) break;
+          if (!c->cv_pop.wait_until(lk, deadline, [&] { return c->stop || !c->queue.empty(); })) break;
+        }
+      }
+      r = enqueue_async(c, group);
       if (r == SNB_OK) continue;
     } else {
       while (c->n_enq != c->n_ret) retire_oldest(c);   // larger than one pass: chunked synchronous path
-      r = infer_host(c, t.in, nullptr, t.out, t.batch);
+      r = infer_host(c, group[0].in, nullptr, group[0].out, group[0].batch);
     }
     snb_rt_stat st = c->stat;
-    if (t.done) t.done(t.user, r, &st);
+    for (const Task& t : group)
+      if (t.done) t.done(t.user, r, &st);
     {
       std::unique_lock<std::mutex> lk(c->mu);
-      --c->inflight;
+      c->inflight -= (int)group.size();
     }
     c->cv_push.notify_all();
   }

@@ -57,13 +57,14 @@ struct Task {
   const int8_t* in; int32_t* out; int batch; snb_done_fn done; void* user;
 };
 
-// One in-flight asynchronous call: its own device staging buffers, so the host->device copy of call k+1 and the
-// device->host copy of call k-1 overlap the kernels of call k (three streams, ordered by events).
+// One in-flight asynchronous pass: its own device staging buffers, so the host->device copy of pass k+1 and the
+// device->host copy of pass k-1 overlap the kernels of pass k (three streams, ordered by events).
 struct AsyncSlot {
   int8_t* d_in = nullptr;
   int32_t* d_out = nullptr;
   cudaEvent_t e_in = nullptr, e_done = nullptr, e_out = nullptr;
-  Task task{};
+  std::vector<Task> tasks;             // the calls this pass serves (> 1: coalesced, see worker_main)
+  int batch = 0;                       // pairs of the pass = sum of the calls' batches
   bool busy = false;
   double t0 = 0;
 };
@@ -98,6 +99,7 @@ struct snb_ctx {
 
   std::map<int, cudaGraphExec_t> graphs;   // by batch
   int last_B = 0;
+  uint64_t n_passes = 0;               // whole-network passes launched so far (snb_get_pass_count)
 
   // async tasks (task_num in flight; callbacks on the worker thread = the reference's PostProcess thread)
   std::thread worker;

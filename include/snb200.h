@@ -50,6 +50,7 @@ enum {
   SNB_FLAG_NO_FUSE = 16,      /* diagnostics: residual blocks as two separate convolution launches */
   SNB_FLAG_NO_STREAM = 32,    /* diagnostics: tiled k_conv_tc / CUDA-core kernels instead of the streaming convolution */
   SNB_FLAG_NO_HBMCONV = 128,  /* diagnostics: firstconv.0 on the tcgen05 streaming kernel instead of k_conv_first (k_conv_hbm.cu) */
+  SNB_FLAG_NO_COALESCE = 256, /* snb_infer_async: one pass per call even when max_batch > 1 (default: queued calls are merged into passes of up to max_batch pairs) */
   SNB_FLAG_PIPE = 64          /* experiment: layer2's identity blocks as one layer-pipelined launch (k_conv_pipe.cu; correct but slower) */
 };
 
@@ -133,6 +134,9 @@ SNB_API int snb_infer_device(snb_ctx* ctx, const int8_t* d_in, int32_t* d_out, i
  * frames: batch x side-by-side NV12 [H*3/2, 2W] host memory. */
 SNB_API int snb_infer_nv12(snb_ctx* ctx, const uint8_t* frames, int32_t* out, int32_t batch);
 
+/* Whole-network passes launched so far (each = kernel_launches kernels).  With coalescing a pass can serve several
+ * snb_infer_async calls, so passes <= calls. */
+SNB_API int64_t snb_get_pass_count(const snb_ctx* ctx);
 SNB_API int snb_get_rt_stat(const snb_ctx* ctx, snb_rt_stat* stat);
 SNB_API const char* snb_last_error(const snb_ctx* ctx);   /* ctx may be NULL: last create error */
 SNB_API const char* snb_version(void);

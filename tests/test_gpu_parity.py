@@ -105,6 +105,50 @@ def test_async_api(built_lib):
     m.close()
 
 
+@pytest.mark.parametrize("flags_name", ["coalesce", "no_coalesce"])
+def test_async_calls_coalesced_into_batched_passes(built_lib, flags_name):
+    """max_batch > 1: the worker merges queued snb_infer_async calls into passes of up to max_batch pairs (two passes in
+    flight).  Per-call semantics must not change: every call gets ITS result (bit-identical to the synchronous call,
+    whatever pass and position it lands in), its own callback, in submission order."""
+    from hobot_stereonet_b200 import capi
+    H, W, K, D = 48, 64, 3, 6
+    cfg = arch.Config(H, W, K, D)
+    n = 23
+    s8 = [pp.cvt_nv12_to_tensor_fast(*pp.split_side_by_side_nv12(synth.frame(H, W, cfg.max_disp, seed=160 + i), H, 2 * W), W, H)
+          for i in range(n)]
+    flags = capi.FLAG_NO_COALESCE if flags_name == "no_coalesce" else 0
+    m = _model(H, W, K, D, task_num=4, max_batch=3, flags=flags)
+    want = [m.infer(x) for x in s8]
+    outs = [np.zeros((1, 1, H, W), np.int32) for _ in s8]
+    seen, lock = [], threading.Lock()
+
+    def done(i):
+        def f(status, stat):
+            with lock:
+                seen.append((i, status))
+        return f
+
+    for rep in range(2):                       # second round: slots and graphs of every batch size already exist
+        seen.clear()
+        for o in outs:
+            o[:] = 0
+        for i, x in enumerate(s8):
+            m.infer_async(x, outs[i], done(i))
+            if i == 9:
+                m.wait_all()                   # drain in the middle: the worker goes idle and restarts
+        m.wait_all()
+        assert [i for i, _ in seen] == list(range(n)) and all(s == 0 for _, s in seen)
+        assert all((a == b).all() for a, b in zip(outs, want))
+    # a call that is itself a batch of 2 coalesces with a single (2 + 1 <= 3) and keeps its layout
+    pair = np.concatenate([s8[0], s8[1]])
+    out2, out1 = np.zeros((2, 1, H, W), np.int32), np.zeros((1, 1, H, W), np.int32)
+    m.infer_async(pair, out2)
+    m.infer_async(s8[2], out1)
+    m.wait_all()
+    assert (out2[0:1] == want[0]).all() and (out2[1:2] == want[1]).all() and (out1 == want[2]).all()
+    m.close()
+
+
 def test_io_properties_and_errors(built_lib):
     from hobot_stereonet_b200 import Model, SnbError, capi
     m = _model(64, 96, 3, 8)
