@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("SNB_PRECISION", "tc"), choices=["fp32", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs under ncu only: device-resident loop, no e2e legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -184,7 +185,7 @@ def main():
     m = Model(H, W, K, D, max_batch=BATCH, device=local_rank, task_num=4, precision=prec, weights=blob)
     # the e2e leg's context: same network, same one-pair calls, but room for the library to merge queued snb_infer_async
     # calls into passes of up to COALESCE_MAX pairs (capi.cu worker_main)
-    mc = Model(H, W, K, D, max_batch=COALESCE_MAX, device=local_rank, task_num=4, precision=prec, weights=blob)
+    mc = None if args.no_e2e else Model(H, W, K, D, max_batch=COALESCE_MAX, device=local_rank, task_num=4, precision=prec, weights=blob)
     del blob
 
     # ---- inputs: a rotating pool larger than L2, so no step finds its input cached ----
@@ -221,38 +222,40 @@ def main():
         torch.cuda.synchronize(dev)
         ms = ev0.elapsed_time(ev1)
         barrier()
-        # ---- e2e: the reference-facing call with HOST buffers.  The node calls DnnNode::Run(is_sync=false) with
-        # task_num = 4 calls in flight (stereonet_node.cpp:144,812): snb_infer_async, pinned buffers, copies timed.
-        for i in range(3):
-            m.infer(host_in[i:i + 1].numpy(), host_out[i:i + 1].numpy())
-        for i in range(12):                              # warm the e2e context: graphs of every pass size it will use
-            mc.infer_async(host_in[i:i + 1].numpy(), host_out[i:i + 1].numpy())
-        mc.wait_all()
-        barrier()
-        passes0 = mc.pass_count()
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            j = (3 + i) % pool_n
-            mc.infer_async(host_in[j:j + 1].numpy(), host_out[j:j + 1].numpy())
-        mc.wait_all()
-        torch.cuda.synchronize(dev)
-        e2e_s = time.perf_counter() - t0
-        e2e_passes = mc.pass_count() - passes0
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(args.steps):                      # same calls, one pass per call (max_batch = 1 context)
-            j = (3 + i) % pool_n
-            m.infer_async(host_in[j:j + 1].numpy(), host_out[j:j + 1].numpy())
-        m.wait_all()
-        torch.cuda.synchronize(dev)
-        e2e_1_s = time.perf_counter() - t0
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(args.steps):                      # same through the synchronous call, one pair in flight
-            j = (3 + i) % pool_n
-            m.infer(host_in[j:j + 1].numpy(), host_out[j:j + 1].numpy())
-        torch.cuda.synchronize(dev)
-        e2e_sync_s = time.perf_counter() - t0
+        e2e_s = e2e_1_s = e2e_sync_s = float('nan'); e2e_passes = 0
+        if not args.no_e2e:
+            # ---- e2e: the reference-facing call with HOST buffers.  The node calls DnnNode::Run(is_sync=false) with
+            # task_num = 4 calls in flight (stereonet_node.cpp:144,812): snb_infer_async, pinned buffers, copies timed.
+            for i in range(3):
+                m.infer(host_in[i:i + 1].numpy(), host_out[i:i + 1].numpy())
+            for i in range(12):                              # warm the e2e context: graphs of every pass size it will use
+                mc.infer_async(host_in[i:i + 1].numpy(), host_out[i:i + 1].numpy())
+            mc.wait_all()
+            barrier()
+            passes0 = mc.pass_count()
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                j = (3 + i) % pool_n
+                mc.infer_async(host_in[j:j + 1].numpy(), host_out[j:j + 1].numpy())
+            mc.wait_all()
+            torch.cuda.synchronize(dev)
+            e2e_s = time.perf_counter() - t0
+            e2e_passes = mc.pass_count() - passes0
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(args.steps):                      # same calls, one pass per call (max_batch = 1 context)
+                j = (3 + i) % pool_n
+                m.infer_async(host_in[j:j + 1].numpy(), host_out[j:j + 1].numpy())
+            m.wait_all()
+            torch.cuda.synchronize(dev)
+            e2e_1_s = time.perf_counter() - t0
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(args.steps):                      # same through the synchronous call, one pair in flight
+                j = (3 + i) % pool_n
+                m.infer(host_in[j:j + 1].numpy(), host_out[j:j + 1].numpy())
+            torch.cuda.synchronize(dev)
+            e2e_sync_s = time.perf_counter() - t0
     clocks = clk.summary()
     launches_per_step = m.rt_stat().kernel_launches
 
@@ -318,9 +321,11 @@ def main():
                     "one_pass_per_call_api": "snb_infer_async on a max_batch = 1 context (no merging), 4 calls in flight",
                     "sync_value": world * args.steps * BATCH / (e2e_sync_ms * 1e-3), "sync_api": "snb_infer (one call in flight)"},
             # device-resident loop + one-pass-per-call async loop + sync loop, and the merged passes of the e2e loop (rank 0)
-            "gpu_launches": launches_per_step * (args.steps * 3 + e2e_passes),
+            "gpu_launches": launches_per_step * (args.steps * (1 if args.no_e2e else 3) + e2e_passes),
             "clocks": clocks, "roofline": roofline,
         }
+        if args.no_e2e:
+            result["e2e"] = None                             # profiling run: no e2e legs were executed
         if not args.no_cpu_baseline and world == 1:
             result["cpu_baseline"] = cpu_baseline()
     m.close()

@@ -63,7 +63,9 @@ int DnnNode::Init() {
   memset(&cfg, 0, sizeof(cfg));
   cfg.struct_size = sizeof(cfg);
   cfg.height = p.model_in_h; cfg.width = p.model_in_w; cfg.K = p.K; cfg.D = p.D;
-  cfg.max_batch = 1;                 // one frame per Run(), as the reference
+  // one frame per Run(), as the reference - but up to task_num frames may be in flight (stereonet_node.cpp:144), and the
+  // library merges the queued ones into one pass (capi.cu worker_main): room for that many pairs per pass
+  cfg.max_batch = p.task_num > 1 ? (p.task_num < 4 ? p.task_num : 4) : 1;
   cfg.device = p.device;
   cfg.task_num = p.task_num;
   cfg.precision = p.precision;
