@@ -105,27 +105,25 @@ struct CostvolParams {
   int dsplit;            // CTAs sharing one (row, pair, block): each emits D / dsplit hypotheses (more CTAs in flight)
 };
 
+// One CTA = one feature row x one (correlation block, concat block) pair q x one slice of the D hypotheses.  A thread owns
+// pixel x: the eight 8-channel groups of ITS left feature live in registers for all d, the right feature row sits in shared
+// memory as [group][channel half][x][4] (conflict-free 128-bit loads at x - d), and every (x, d) leaves as whole 16-byte
+// vectors: consecutive threads write consecutive pixels of a [cb][d][y] row.
 template <typename T>
-__global__ void __launch_bounds__(256) k_costvol(CostvolParams p) {
+__global__ void __launch_bounds__(128) k_costvol(CostvolParams p) {
   pdl_trigger();
   pdl_wait();
-  extern __shared__ float sm[];
+  extern __shared__ float sR[];                                   // [8 j][2 halves][w][4]
   const int y = blockIdx.x, b = blockIdx.y, q = blockIdx.z & 3, dpart = blockIdx.z >> 2;    // q in 0..3
   const int dper = (p.D + p.dsplit - 1) / p.dsplit, d_lo = dpart * dper, d_hi = min(p.D, d_lo + dper);
-  const int w = p.w, h = p.h, D = p.D;
-  const int pitch = w * 8 + 4;                                  // +4 floats: 8 blocks hit 8 distinct 16B lanes
-  float* sL = sm;                  // [8][pitch]
-  float* sR = sm + 8 * pitch;
+  const int w = p.w, D = p.D;
+  const size_t goff = (size_t)(q * 8) * p.gwc.slice + (size_t)y * p.gwc.ws * 8;      // block q*8 + j adds j * slice
   for (int i = threadIdx.x; i < 8 * w; i += blockDim.x) {
-    const int j = i / w, x = i % w;
-    const size_t off = (size_t)(q * 8 + j) * p.gwc.slice + ((size_t)y * p.gwc.ws + x) * 8;
+    const int j = i / w, x = i - j * w;
     float v[8];
-    St<T>::ld8(p.gwc.p, (size_t)b * p.gwc.ss + off, p.gwc.lo, v);
-    reinterpret_cast<float4*>(sL + j * pitch + x * 8)[0] = make_float4(v[0], v[1], v[2], v[3]);
-    reinterpret_cast<float4*>(sL + j * pitch + x * 8)[1] = make_float4(v[4], v[5], v[6], v[7]);
-    St<T>::ld8(p.gwc.p, (size_t)(p.B + b) * p.gwc.ss + off, p.gwc.lo, v);
-    reinterpret_cast<float4*>(sR + j * pitch + x * 8)[0] = make_float4(v[0], v[1], v[2], v[3]);
-    reinterpret_cast<float4*>(sR + j * pitch + x * 8)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    St<T>::ld8(p.gwc.p, (size_t)(p.B + b) * p.gwc.ss + goff + (size_t)j * p.gwc.slice + (size_t)x * 8, p.gwc.lo, v);
+    *reinterpret_cast<float4*>(sR + ((j * 2 + 0) * w + x) * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(sR + ((j * 2 + 1) * w + x) * 4) = make_float4(v[4], v[5], v[6], v[7]);
   }
   __syncthreads();
 
@@ -134,40 +132,56 @@ __global__ void __launch_bounds__(256) k_costvol(CostvolParams p) {
   const size_t vc = (size_t)b * p.vol.ss + (size_t)q * D * vslice + (size_t)y * p.vol.ws * 8;         // concat block q
   const size_t csrc = (size_t)((q >> 1) ? p.B + b : b) * p.cat.ss + (size_t)(q & 1) * p.cat.slice + (size_t)y * p.cat.ws * 8;
   const bool shifted = (q >> 1) != 0;
+  const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 
-  for (int e = threadIdx.x; e < w * 8; e += blockDim.x) {
-    const int x = e >> 3, j = e & 7;
-    const float4 l0 = *reinterpret_cast<const float4*>(sL + j * pitch + x * 8);
-    const float4 l1 = *reinterpret_cast<const float4*>(sL + j * pitch + x * 8 + 4);
-    const float cl = St<T>::ld1(p.cat.p, csrc + e, p.cat.lo);      // unshifted concat value (left blocks)
+  for (int x = threadIdx.x; x < w; x += blockDim.x) {
+    float L[8][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) St<T>::ld8(p.gwc.p, (size_t)b * p.gwc.ss + goff + (size_t)j * p.gwc.slice + (size_t)x * 8, p.gwc.lo, L[j]);
+    float cl[8];
+    St<T>::ld8(p.cat.p, csrc + (size_t)x * 8, p.cat.lo, cl);       // unshifted concat block (left feature)
     for (int d = d_lo; d < d_hi; ++d) {
-      float g = 0.f, c = 0.f;
       if (x >= d) {
-        const float4 r0 = *reinterpret_cast<const float4*>(sR + j * pitch + (x - d) * 8);
-        const float4 r1 = *reinterpret_cast<const float4*>(sR + j * pitch + (x - d) * 8 + 4);
-        g = l0.x * r0.x;
-        g = fmaf(l0.y, r0.y, g); g = fmaf(l0.z, r0.z, g); g = fmaf(l0.w, r0.w, g);
-        g = fmaf(l1.x, r1.x, g); g = fmaf(l1.y, r1.y, g); g = fmaf(l1.z, r1.z, g); g = fmaf(l1.w, r1.w, g);
-        g *= 0.125f;
-        c = shifted ? St<T>::ld1(p.cat.p, csrc + e - d * 8, p.cat.lo) : cl;
+        float g[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 r0 = *reinterpret_cast<const float4*>(sR + ((j * 2 + 0) * w + (x - d)) * 4);
+          const float4 r1 = *reinterpret_cast<const float4*>(sR + ((j * 2 + 1) * w + (x - d)) * 4);
+          float a = L[j][0] * r0.x;
+          a = fmaf(L[j][1], r0.y, a); a = fmaf(L[j][2], r0.z, a); a = fmaf(L[j][3], r0.w, a);
+          a = fmaf(L[j][4], r1.x, a); a = fmaf(L[j][5], r1.y, a); a = fmaf(L[j][6], r1.z, a); a = fmaf(L[j][7], r1.w, a);
+          g[j] = a * 0.125f;
+        }
+        St<T>::st8(p.vol.p, vg + (size_t)d * vslice + (size_t)x * 8, p.vol.lo, g);
+        if (shifted) {
+          float cr[8];
+          St<T>::ld8(p.cat.p, csrc + (size_t)(x - d) * 8, p.cat.lo, cr);
+          St<T>::st8(p.vol.p, vc + (size_t)d * vslice + (size_t)x * 8, p.vol.lo, cr);
+        } else {
+          St<T>::st8(p.vol.p, vc + (size_t)d * vslice + (size_t)x * 8, p.vol.lo, cl);
+        }
+      } else {
+        St<T>::st8(p.vol.p, vg + (size_t)d * vslice + (size_t)x * 8, p.vol.lo, zero8);
+        St<T>::st8(p.vol.p, vc + (size_t)d * vslice + (size_t)x * 8, p.vol.lo, zero8);
       }
-      St<T>::st1(p.vol.p, vg + (size_t)d * vslice + e, p.vol.lo, g);
-      St<T>::st1(p.vol.p, vc + (size_t)d * vslice + e, p.vol.lo, c);
     }
   }
 }
 
 cudaError_t launch_costvol(Tens gwc, Tens cat, Tens vol, int B, int D, cudaStream_t st) {
   const int h = gwc.h, w = gwc.w;
-  const size_t smem = (size_t)2 * 8 * (w * 8 + 4) * sizeof(float);
-  const int dsplit = D >= 12 ? 3 : 1;
+  const size_t smem = (size_t)8 * 2 * w * 4 * sizeof(float);
+  static const int env_split = getenv("SNB_COSTVOL_DSPLIT") ? atoi(getenv("SNB_COSTVOL_DSPLIT")) : 0;
+  // measured at config 2 (D = 24, 272 CTAs at dsplit 1): 20.5 us at dsplit 1, 24.5 at 2, 23.3 at 3, 30.9 at 6 - every extra
+  // slice re-stages the right feature row; long D gets one slice per 48 hypotheses
+  const int dsplit = env_split > 0 ? std::min(env_split, D) : std::max(1, std::min(8, D / 48));
   CostvolParams p{view(gwc), view(cat), view(vol), B, D, h, w, dsplit};
   if (vol.planes == 2) {
     if (need_attr(5)) cudaFuncSetAttribute(k_costvol<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    launch_k(k_costvol<__half>, dim3(h, B, 4 * dsplit), 256, smem, st, p);
+    launch_k(k_costvol<__half>, dim3(h, B, 4 * dsplit), 128, smem, st, p);
   } else {
     if (need_attr(2)) cudaFuncSetAttribute(k_costvol<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    launch_k(k_costvol<float>, dim3(h, B, 4 * dsplit), 256, smem, st, p);
+    launch_k(k_costvol<float>, dim3(h, B, 4 * dsplit), 128, smem, st, p);
   }
   return cudaGetLastError();
 }
