@@ -32,10 +32,13 @@ L2_BYTES = 126 * 1024 * 1024
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
 # `ncu --set full` capture (profiles/): filled in by hand after each capture, None when not captured.
 TRAFFIC = {
-    # profiles/r01_final_ncu_full_resblock.csv: one full-resolution refinement block (algorithmic 134 MB)
-    "k_resblock_tc": 106.2e6,
-    # profiles/r01_final_ncu_full_stream.csv: firstconv.0 (algorithmic 33.4 MB in + 16.7 MB out, the output stays in L2)
-    "k_conv_stream": 34.7e6,
+    # profiles/r01_final_ncu_full_resblock.csv: one full-resolution refinement block, 78.8 + 27.2 MB (algorithmic 134 MB:
+    # part of the output is still in L2 when the kernel ends)
+    "k_resblock_tc": 106.0e6,
+    # profiles/r01_final_ncu_full_stream.csv: layer2.1.conv_a / conv_b, the shape of 30 of the 58 launches: 4.6 / 9.0 MB read,
+    # 0 written (algorithmic 8.4 MB in + 8.4 MB out (+ 8.4 MB residual): the 68x120 maps live in L2 between launches);
+    # head.filter.1 (profiles/r01_final_ncu_full_stream3d.csv): 26.9 MB read for 25 MB in + 25 MB out
+    "k_conv_stream": 6.8e6,
 }
 
 
@@ -296,6 +299,8 @@ def main():
         roofline = {"kernel": dom + (" (fused residual block: conv+ReLU+conv+residual+ReLU, tcgen05, split-fp16 operands = 3 fp16 MMAs per algorithmic MAC)"
                                      if dom == "k_resblock_tc" else ""),
                     "bound": "tensor", "achieved": tf(d), "peak": tf_peak, "unit": "TFLOP/s", "frac": tf(d) / tf_peak,
+                    # split-fp16 operands: 3 fp16 MMAs are issued per algorithmic MAC, so the tensor pipe works at 3 x frac
+                    "fp16_mma_issued_frac": 3 * tf(d) / tf_peak,
                     "traffic": TRAFFIC.get(dom), "peak_source": peak_src, "launches": d[3], "share_of_step": d[0] / total_ms,
                     "algorithmic_flops_per_launch": d[1] / max(d[3], 1), "avg_launch_ms": d[0] / max(d[3], 1),
                     "families": {k: {"ms": v[0], "share": v[0] / total_ms, "launches": v[3],

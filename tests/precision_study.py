@@ -36,6 +36,10 @@ def main():
         "bf16 refine only": only(["head.refine"], b16),
         "refine: fp16 weights, exact act": lambda t, n: h16(t) if n.startswith("head.refine") and n.endswith(":w") else t,
         "refine: fp16 act, exact weights": lambda t, n: h16(t) if n.startswith("head.refine") and n.endswith(":a") else t,
+        "refine.(K-1): fp16 act, exact weights": lambda t, n: h16(t) if n.startswith(f"head.refine.{K - 1}") and n.endswith(":a") else t,
+        "refine.(K-1).blocks: fp16 act, exact weights": lambda t, n: h16(t) if n.startswith(f"head.refine.{K - 1}.blocks") and n.endswith(":a") else t,
+        "refine.*.blocks: fp16 act, exact weights": lambda t, n: h16(t) if n.startswith("head.refine") and ".blocks." in n and n.endswith(":a") else t,
+        "refine.(K-1).blocks: fp16 weights, exact act": lambda t, n: h16(t) if n.startswith(f"head.refine.{K - 1}.blocks") and n.endswith(":w") else t,
         "agg3d: fp16 weights, exact act": lambda t, n: h16(t) if n.startswith("head.filter") and n.endswith(":w") else t,
         "agg3d: fp16 act, exact weights": lambda t, n: h16(t) if n.startswith("head.filter") and n.endswith(":a") else t,
         "backbone: fp16 weights, exact act": lambda t, n: h16(t) if n.startswith("backbone") and n.endswith(":w") else t,
