@@ -30,6 +30,10 @@ cudaError_t conv_pipe_plan(CsPlan* plan, const Tens& in, int ch, int num_sms);
 int conv_pipe_layers_per_launch(const CsPlan& plan, int N, int nlayers);
 cudaError_t launch_conv_pipe(const CsPlan& plan, int N, const CsLayer* d_layers, int nlayers, int* d_done, cudaStream_t st);
 
+// k_conv_pair.cu — one 64-channel BasicBlock (conv_a + conv_b) as one launch of thread-block clusters, y rows through DSMEM (M1: layer2)
+cudaError_t conv_pair_plan(CsPlan* plan, const Tens& in, int ch, int num_sms);
+cudaError_t launch_conv_pair(const CsPlan& plan, int N, const CsLayer& la, const CsLayer& lb, cudaStream_t st);
+
 // k_conv_hbm.cu — few-input-channel convolutions of the tensor path (firstconv.0, refinement conv_in): CUDA cores, weights in the constant bank
 void conv_first_pack(const float* W, const float* bias, int cin, ConvFirstParams* p);
 cudaError_t launch_conv_first(const ConvFirstParams& p, int N, cudaStream_t st);

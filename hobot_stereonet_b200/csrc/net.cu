@@ -239,6 +239,35 @@ struct Builder {
     return out;
   }
 
+  // one identity BasicBlock (conv_a -> ReLU -> conv_b -> + x -> ReLU) of 64 channels as ONE cluster launch (k_conv_pair.cu)
+  bool pair(const std::string& prefix, const Tens& x, int nmul, int dil, Tens* result) {
+    static const int env_pair = getenv("SNB_PAIR") ? atoi(getenv("SNB_PAIR")) : -1;
+    // opt-in: 15 us in-kernel per block against 2 x 7 us, but a cluster launch costs ~5 us more than a plain one inside the
+    // CUDA graph: 1.646 ms per pass with it, 1.573 without (k_conv_pair.cu header)
+    const bool want = env_pair >= 0 ? env_pair != 0 : (c->cfg.flags & SNB_FLAG_PAIR) != 0;
+    if (c->planes != 2 || !want || (c->cfg.flags & (SNB_FLAG_NO_TENSOR | SNB_FLAG_NO_STREAM | SNB_FLAG_KEEP_STAGES)) || dil != 1) return false;
+    auto ia = c->convs.find(prefix + ".conv_a"), ib = c->convs.find(prefix + ".conv_b");
+    if (ia == c->convs.end() || ib == c->convs.end() || ia->second.cin != x.c || ia->second.cout != x.c || ib->second.cin != x.c ||
+        ib->second.cout != x.c || ia->second.ks != 3 || ib->second.ks != 3 || ia->second.kz != 1) return false;
+    CsPlan plan;
+    if (conv_pair_plan(&plan, x, x.c, c->num_sms) != cudaSuccess) return false;
+    Tens o = alloc(nmul, x.c, 1, x.h, x.w, x.pad);
+    CsLayer la{}, lb{};
+    la.in = view(x); la.w = stream_weights(prefix + ".conv_a", ia->second, 32); la.bias = ia->second.b; la.relu = 1;
+    lb.out = view(o); lb.res = view(x); lb.has_res = 1; lb.w = stream_weights(prefix + ".conv_b", ib->second, 32);
+    lb.bias = ib->second.b; lb.relu = 1;
+    if (!la.w || !lb.w) return false;
+    Op op; op.name = prefix + " [tc-pair]";
+    const double px = (double)nmul * x.h * x.w;
+    op.flops = 2 * 2.0 * px * x.c * x.c * 9;
+    op.bytes = 4.0 * px * x.c * 3;
+    op.fn = [plan, la, lb, nmul](int B, cudaStream_t st) { return launch_conv_pair(plan, nmul * B, la, lb, st); };
+    c->n_tc_convs += 2;
+    c->ops.push_back(op);
+    *result = o;
+    return true;
+  }
+
   // blocks [first, first + nblk) of `layer` (identity BasicBlocks on tensors of x's geometry) as a layer pipeline
   // (k_conv_pipe.cu): one CTA per (convolution, view, strip, channel slice), rows handed from layer to layer through L2
   bool chain(const std::string& layer, int first, int nblk, const Tens& x, int nmul, int dil, Tens* result) {
@@ -455,6 +484,14 @@ int build_plan(snb_ctx* c) {
           b.free(x);
           x = o;
           break;
+        }
+      }
+      if (bi >= 1 && s == 1) {
+        Tens o;
+        if (b.pair(p, x, 2, dil, &o)) {
+          b.free(x);
+          x = o;
+          continue;
         }
       }
       Tens sc = x;
