@@ -123,7 +123,10 @@ SNB_API int snb_get_model_input_size(const snb_ctx* ctx, int32_t input_index, in
  * value * 2.60443857769133e-06 * 192 = left-view disparity in pixels. */
 SNB_API int snb_infer(snb_ctx* ctx, const int8_t* in, int32_t* out, int32_t batch);
 /* is_sync_mode=false: returns after enqueueing; `done` fires on a library-owned thread (the
- * reference's PostProcess thread).  Blocks up to timeout_ms (-1: forever) for a free task slot. */
+ * reference's PostProcess thread).  Blocks up to timeout_ms (-1: forever) for a free task slot.
+ * On a context with max_batch > 1 the library may serve several queued calls with ONE pass over the network (up to
+ * max_batch pairs; SNB_FLAG_NO_COALESCE turns that off).  Nothing changes per call: own buffers, own callback,
+ * callbacks in submission order, results bit-identical to snb_infer. */
 SNB_API int snb_infer_async(snb_ctx* ctx, const int8_t* in, int32_t* out, int32_t batch,
                             snb_done_fn done, void* user, int32_t timeout_ms);
 SNB_API int snb_wait_all(snb_ctx* ctx);
