@@ -231,7 +231,9 @@ def main():
             # task_num = 4 calls in flight (stereonet_node.cpp:144,812): snb_infer_async, pinned buffers, copies timed.
             for i in range(3):
                 m.infer(host_in[i:i + 1].numpy(), host_out[i:i + 1].numpy())
-            for i in range(12):                              # warm the e2e context: graphs of every pass size it will use
+            for b in range(1, COALESCE_MAX + 1):             # warm the e2e context: the CUDA graph of every pass size it may use
+                mc.infer(host_in[0:b].numpy(), host_out[0:b].numpy())
+            for i in range(12):
                 mc.infer_async(host_in[i:i + 1].numpy(), host_out[i:i + 1].numpy())
             mc.wait_all()
             barrier()
