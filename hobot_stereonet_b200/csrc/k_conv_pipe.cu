@@ -190,12 +190,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) k_conv_pipe(const CsParams p, c
         tc_fence_after();
         const uint64_t a_hi = a_desc0 + (uint64_t)slot * a_slot16, a_lo = a_hi + a_lo_off;
         if (leader) {
-          umma_f16(dcol, a_hi, w_hi, idesc2, acc);                       // [main | corr] (+)= A_hi x [W_hi | W_lo]
-          umma_f16_acc(dcol + NCOL, a_lo, w_hi, idesc);                  // corr += A_lo x W_hi
-          umma_f16_acc(dcol, a_hi + dil16, w_hi + wkx16, idesc2);
-          umma_f16_acc(dcol + NCOL, a_lo + dil16, w_hi + wkx16, idesc);
-          umma_f16_acc(dcol, a_hi + 2 * dil16, w_hi + 2 * wkx16, idesc2);
-          umma_f16_acc(dcol + NCOL, a_lo + 2 * dil16, w_hi + 2 * wkx16, idesc);
+          cs_issue_split(dcol, a_hi, a_lo, w_hi, dil16, wkx16, idesc, idesc2, acc);
           umma_commit(&x_empty[slot]);
         }
         __syncwarp();
@@ -241,19 +236,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) k_conv_pipe(const CsParams p, c
       if (++ts == CP_SLOTS) { ts = 0; fpar ^= 1; }
       // drain first (the finished row goes to f, the partial rows roll over), hand the slot back, then emit
       float f[32];
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        float v0[16], v1[16], v2[16], c0[16], c1[16], c2[16];
-        const uint32_t col = lane_addr + ts_cur * SLOT_STRIDE + hf * 16;
-        cs_ld3x16(col, col + 32, col + 64, v0, v1, v2);
-        cs_ld3x16(col + NCOL, col + NCOL + 32, col + NCOL + 64, c0, c1, c2);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          f[hf * 16 + c] = a0[hf * 16 + c] + (v2[c] + c2[c]);
-          a0[hf * 16 + c] = a1[hf * 16 + c] + (v1[c] + c1[c]);
-          a1[hf * 16 + c] = (v0[c] + c0[c]) + s_bias[hf * 16 + c];
-        }
-      }
+      cs_drain_split(lane_addr + ts_cur * SLOT_STRIDE, a0, a1, f, s_bias);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[ts_cur]);

@@ -164,12 +164,7 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
             const uint64_t a_hi = a_desc0 + (uint64_t)slot * a_slot16, a_lo = a_hi + a_lo_off;
             if (leader) {
               if constexpr (SPLIT) {
-                umma_f16(dcol, a_hi, w_hi, idesc2, acc);                       // [main | corr] (+)= A_hi x [W_hi | W_lo]
-                umma_f16_acc(dcol + NCOL, a_lo, w_hi, idesc);                  // corr += A_lo x W_hi
-                umma_f16_acc(dcol, a_hi + dil16, w_hi + wkx16, idesc2);
-                umma_f16_acc(dcol + NCOL, a_lo + dil16, w_hi + wkx16, idesc);
-                umma_f16_acc(dcol, a_hi + 2 * dil16, w_hi + 2 * wkx16, idesc2);
-                umma_f16_acc(dcol + NCOL, a_lo + 2 * dil16, w_hi + 2 * wkx16, idesc);
+                cs_issue_split(dcol, a_hi, a_lo, w_hi, dil16, wkx16, idesc, idesc2, acc);
               } else if constexpr (NCO == 16) {
                 // one real output channel: W_hi | W_lo share a 16-column group (columns 0, 1), the second weight block
                 // holds W_hi in column 2 for the lo plane: 2 MMAs per tap, hi*hi | hi*lo | lo*hi in columns 0 | 1 | 2

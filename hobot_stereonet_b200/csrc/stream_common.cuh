@@ -1,4 +1,4 @@
-// Helpers shared by the streaming tcgen05 convolution kernels (k_conv_stream.cu, k_conv_pipe.cu).
+// Helpers shared by the streaming tcgen05 convolution kernels (k_conv_stream.cu, k_conv_pipe.cu, k_conv_pair.cu).
 #pragma once
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -43,6 +43,38 @@ __device__ __forceinline__ void cs_ld3x16(uint32_t c0, uint32_t c1, uint32_t c2,
       : "r"(c0), "r"(c1), "r"(c2) : "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) { v0[i] = __uint_as_float(r[i]); v1[i] = __uint_as_float(r[16 + i]); v2[i] = __uint_as_float(r[32 + i]); }
+}
+
+// One 16-channel chunk of a SPLIT job (NCOL = 96 accumulator columns per half): [main | corr] (+)= A_hi x [W_hi | W_lo] at
+// N = 192 and corr += A_lo x W_hi at N = 96, for the three kernel columns (A shifted by `dil16`, weights by `wkx16`).
+__device__ __forceinline__ void cs_issue_split(uint32_t dcol, uint64_t a_hi, uint64_t a_lo, uint64_t w_hi, uint64_t dil16,
+                                               uint64_t wkx16, uint32_t idesc, uint32_t idesc2, uint32_t acc) {
+  constexpr uint32_t NCOL = 96;
+  umma_f16(dcol, a_hi, w_hi, idesc2, acc);
+  umma_f16_acc(dcol + NCOL, a_lo, w_hi, idesc);
+  umma_f16_acc(dcol, a_hi + dil16, w_hi + wkx16, idesc2);
+  umma_f16_acc(dcol + NCOL, a_lo + dil16, w_hi + wkx16, idesc);
+  umma_f16_acc(dcol, a_hi + 2 * dil16, w_hi + 2 * wkx16, idesc2);
+  umma_f16_acc(dcol + NCOL, a_lo + 2 * dil16, w_hi + 2 * wkx16, idesc);
+}
+
+// Drain one SPLIT job (main at `col0`, corr 96 columns further, each [ky][32 channels]): the finished output row goes to f,
+// the two partial rows roll over (a new one is born with the bias).
+__device__ __forceinline__ void cs_drain_split(uint32_t col0, float (&a0)[32], float (&a1)[32], float (&f)[32], const float* s_bias) {
+  constexpr uint32_t NCOL = 96;
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    float v0[16], v1[16], v2[16], c0[16], c1[16], c2[16];
+    const uint32_t col = col0 + hf * 16;
+    cs_ld3x16(col, col + 32, col + 64, v0, v1, v2);
+    cs_ld3x16(col + NCOL, col + NCOL + 32, col + NCOL + 64, c0, c1, c2);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      f[hf * 16 + c] = a0[hf * 16 + c] + (v2[c] + c2[c]);
+      a0[hf * 16 + c] = a1[hf * 16 + c] + (v1[c] + c1[c]);
+      a1[hf * 16 + c] = (v0[c] + c0[c]) + s_bias[hf * 16 + c];
+    }
+  }
 }
 
 __device__ __forceinline__ void cs_split8(const float* f, uint4& oh, uint4& ol) {
