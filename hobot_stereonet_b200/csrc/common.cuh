@@ -132,7 +132,7 @@ struct RbParams {        // k_resblock_tc.cu: fused 32-channel residual block
   int nxs;               // depth of the x-row ring
   uint32_t sub_bytes, slot_bytes;         // one (plane, chunk) row, one ring slot (8 of them)
   long long* prof;       // SNB_TC_PROF=1: per-CTA cycle counters of the issuer and epilogue roles
-  int dbg;               // timing experiments only (env SNB_RB_DEBUG): 1 no proxy fence, 2 no y stores, 4 no global stores, 8 no residual loads
+  int dbg;               // measurement only (env SNB_RB_DEBUG, full-resolution launches): 16 = drop the A_lo x W_hi products
 };
 struct RbPlan { RbParams p; size_t smem; int num_sms; };
 

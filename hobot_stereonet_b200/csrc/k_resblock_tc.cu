@@ -187,6 +187,8 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
     const uint64_t slot16 = (uint64_t)(p.slot_bytes >> 4), sub16 = (uint64_t)(p.sub_bytes >> 4), wkx16 = (uint64_t)(2 * b_lbo >> 4);
     uint32_t xs = 0, xpar = 0, ys = 0, ypar = 0, apar = 1, bpar = 1, njobs = 0;
 
+    // measurement only (SNB_RB_DEBUG=16, full-resolution launches): drop the A_lo x W_hi products, i.e. fp16-rounded activations
+    const bool no_lo = (p.dbg & 16) != 0;
     // 12 MMAs of one job: A rows at descriptor `a` ([plane][chunk][px][8]), weights at descriptor `w`
     auto issue_job = [&](uint64_t a, uint64_t w, uint32_t dcol) {
 #pragma unroll
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
           const uint64_t sh = (uint64_t)(kx * dil16);
           if (k16 == 0 && kx == 0) umma_f16_zero(dcol, a_hi, db, idesc1);
           else umma_f16_acc(dcol, a_hi + sh, db, idesc1);
-          umma_f16_acc(dcol + RB_SLOT_COLS / 2, a_lo + sh, db, idesc2);
+          if (!no_lo) umma_f16_acc(dcol + RB_SLOT_COLS / 2, a_lo + sh, db, idesc2);
         }
       }
     };
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
           if (k16 == 0 && kx == 0) umma_f16_zero(dcol, a_hi, w_hi, idesc2);
           else umma_f16_acc(dcol, a_hi + sh, w_hi, idesc2);
           umma_f16_acc(dcol, a_hi + sh, w_lo, idesc2);
-          umma_f16_acc(dcol, a_lo + sh, w_hi, idesc2);
+          if (!no_lo) umma_f16_acc(dcol, a_lo + sh, w_hi, idesc2);
         }
       }
     };
@@ -442,6 +444,7 @@ cudaError_t launch_resblock_tc(const RbPlan& plan, int N, const void* wa, const 
                                cudaStream_t st) {
   RbParams p = plan.p;
   p.N = N; p.wa = static_cast<const __half*>(wa); p.wb = static_cast<const __half*>(wb); p.ba = ba; p.bb = bb;
+  { static const int dbg = getenv("SNB_RB_DEBUG") ? atoi(getenv("SNB_RB_DEBUG")) : 0; p.dbg = (long)p.H * p.W >= 400000 ? dbg : 0; }
   // row chunks: about one unit per SM (every unit pays 4 halo rows, but an idle SM pays more), at least 2 rows each
   const int rc_max = cdiv(p.H, p.dil);
   const int columns = N * p.strips * p.dil;                 // independent column walks
