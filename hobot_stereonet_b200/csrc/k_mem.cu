@@ -10,28 +10,58 @@ namespace snb {
 // ------------------------------------------------------------------------------------------------
 // s8 NCHW [B,6,H,W] -> C8 image [2B][1][Hp][Wp][8].  Restates the tensor semantics the BPU model
 // gives its input: value = s8 * (1/128) (preprocess.cpp:1037), channels 0-2 left, 3-5 right.
+// Four pixels per thread (one 4-byte load per colour plane when the rows allow it).  Split-fp16 storage: s8 / 128 is exact in
+// fp16, so only the hi plane is written - the lo plane of the image tensor is zero from its allocation and nothing else
+// ever writes it (k_pre_nv12 writes the same exact values).
 template <typename T>
-__global__ void k_pre_s8(const int8_t* __restrict__ s8, TV img, int B, int H, int W, int Hp, int Wp) {
+__global__ void __launch_bounds__(128) k_pre_s8(const int8_t* __restrict__ s8, TV img, int B, int H, int W, int Hp, int Wp) {
   pdl_trigger();
   pdl_wait();
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int y = blockIdx.y;
   const int n = blockIdx.z;                  // 0..2B-1
-  if (x >= Wp) return;
+  if (x0 >= Wp) return;
   const int b = n % B, view = n / B;
-  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (x < W && y < H) {
-    const int8_t* src = s8 + (((size_t)b * 6 + view * 3) * H + y) * W + x;
+  float v[4][3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i][0] = v[i][1] = v[i][2] = 0.f;
+  if (y < H && x0 < W) {
     const size_t plane = (size_t)H * W;
-    v[0] = (float)src[0] * 0.0078125f;
-    v[1] = (float)src[plane] * 0.0078125f;
-    v[2] = (float)src[2 * plane] * 0.0078125f;
+    const int8_t* src = s8 + (((size_t)b * 6 + view * 3) * H + y) * W + x0;
+    if ((W & 3) == 0) {                      // rows and planes are 4-byte aligned (x0 + 3 < W follows)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const char4 q = __ldg(reinterpret_cast<const char4*>(src + c * plane));
+        v[0][c] = (float)q.x * 0.0078125f; v[1][c] = (float)q.y * 0.0078125f;
+        v[2][c] = (float)q.z * 0.0078125f; v[3][c] = (float)q.w * 0.0078125f;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (x0 + i < W) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) v[i][c] = (float)src[c * plane + i] * 0.0078125f;
+        }
+    }
   }
-  St<T>::st8(img.p, (size_t)n * img.ss + ((size_t)y * img.ws + x) * 8, img.lo, v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (x0 + i >= Wp) break;
+    const size_t idx = (size_t)n * img.ss + ((size_t)y * img.ws + x0 + i) * 8;
+    if constexpr (sizeof(T) == 2) {
+      const __half2 a = __floats2half2_rn(v[i][0], v[i][1]), c2 = __floats2half2_rn(v[i][2], 0.f);
+      uint4 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&a); o.y = *reinterpret_cast<const uint32_t*>(&c2); o.z = 0u; o.w = 0u;
+      *reinterpret_cast<uint4*>(static_cast<__half*>(img.p) + idx) = o;
+    } else {
+      const float o8[8] = {v[i][0], v[i][1], v[i][2], 0.f, 0.f, 0.f, 0.f, 0.f};
+      St<T>::st8(img.p, idx, img.lo, o8);
+    }
+  }
 }
 
 cudaError_t launch_pre_s8(const int8_t* s8, Tens img, int B, int H, int W, cudaStream_t st) {
-  const dim3 g(cdiv(img.w, 128), img.h, 2 * B);
+  const dim3 g(cdiv(cdiv(img.w, 4), 128), img.h, 2 * B);
   if (img.planes == 2) launch_k(k_pre_s8<__half>, g, 128, 0, st, s8, view(img), B, H, W, img.h, img.w);
   else launch_k(k_pre_s8<float>, g, 128, 0, st, s8, view(img), B, H, W, img.h, img.w);
   return cudaGetLastError();
