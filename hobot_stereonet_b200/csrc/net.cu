@@ -476,7 +476,7 @@ int build_plan(snb_ctx* c) {
     for (int bi = 0; bi < LAYER_BLOCKS[li - 1]; ++bi) {
       const std::string p = "backbone.layer" + std::to_string(li) + "." + std::to_string(bi);
       const int s = bi == 0 ? strides[li - 1] : 1, dil = li == 4 ? 2 : 1;
-      // the identity blocks of a layer as ONE persistent launch when two weight slices fit in shared memory (layer2)
+      // opt-in experiments for layer2's identity blocks: all of them as one layer-pipelined launch (SNB_FLAG_PIPE) ...
       if (bi == 1 && li == 2) {
         const int nblk = LAYER_BLOCKS[li - 1] - 1;
         Tens o;
@@ -486,7 +486,8 @@ int build_plan(snb_ctx* c) {
           break;
         }
       }
-      if (bi >= 1 && s == 1) {
+      // ... or each of them as one thread-block-cluster launch (SNB_FLAG_PAIR)
+      if (li == 2 && bi >= 1 && s == 1) {
         Tens o;
         if (b.pair(p, x, 2, dil, &o)) {
           b.free(x);
