@@ -255,6 +255,20 @@ cudaError_t launch_softargmin(Plane cost, Plane disp, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // M5 glue: channel 0 = x2 bilinear upsample of the disparity (align_corners=False), channels 1-3 =
 // left image bilinearly resized to the stage resolution (integer factor f: mean of the central 2x2).
+// first three channels of an image pixel: the image tensor (s8 / 128) is exact in fp16, so its lo plane is zero and is
+// not read (half the bytes of St<__half>::ld8); fp32 storage reads one float4
+template <typename T> __device__ __forceinline__ void img_ld3(const void* base, size_t idx, float (&v)[3]);
+template <> __device__ __forceinline__ void img_ld3<float>(const void* base, size_t idx, float (&v)[3]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(base) + idx));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z;
+}
+template <> __device__ __forceinline__ void img_ld3<__half>(const void* base, size_t idx, float (&v)[3]) {
+  const uint2 h = __ldg(reinterpret_cast<const uint2*>(static_cast<const __half*>(base) + idx));
+  const __half2* h2 = reinterpret_cast<const __half2*>(&h);
+  const float2 a = __half22float2(h2[0]), b = __half22float2(h2[1]);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x;
+}
+
 template <typename T>
 __global__ void k_refine_in(const float* __restrict__ disp, TV img, TV out, int h, int w, int f) {
   pdl_trigger();
@@ -275,16 +289,16 @@ __global__ void k_refine_in(const float* __restrict__ disp, TV img, TV out, int 
   const size_t ib = (size_t)b * img.ss;
   const int Wf = img.ws;
   if (f == 1) {
-    float v[8];
-    St<T>::ld8(img.p, ib + ((size_t)y * Wf + x) * 8, img.lo, v);
+    float v[3];
+    img_ld3<T>(img.p, ib + ((size_t)y * Wf + x) * 8, v);
     o[1] = v[0]; o[2] = v[1]; o[3] = v[2];
   } else {
     const int yy = y * f + f / 2 - 1, xx = x * f + f / 2 - 1;
-    float a[8], bq[8], c[8], d[8];
-    St<T>::ld8(img.p, ib + ((size_t)yy * Wf + xx) * 8, img.lo, a);
-    St<T>::ld8(img.p, ib + ((size_t)yy * Wf + xx + 1) * 8, img.lo, bq);
-    St<T>::ld8(img.p, ib + ((size_t)(yy + 1) * Wf + xx) * 8, img.lo, c);
-    St<T>::ld8(img.p, ib + ((size_t)(yy + 1) * Wf + xx + 1) * 8, img.lo, d);
+    float a[3], bq[3], c[3], d[3];
+    img_ld3<T>(img.p, ib + ((size_t)yy * Wf + xx) * 8, a);
+    img_ld3<T>(img.p, ib + ((size_t)yy * Wf + xx + 1) * 8, bq);
+    img_ld3<T>(img.p, ib + ((size_t)(yy + 1) * Wf + xx) * 8, c);
+    img_ld3<T>(img.p, ib + ((size_t)(yy + 1) * Wf + xx + 1) * 8, d);
 #pragma unroll
     for (int k = 0; k < 3; ++k) o[1 + k] = 0.5f * (0.5f * a[k] + 0.5f * bq[k]) + 0.5f * (0.5f * c[k] + 0.5f * d[k]);
   }
