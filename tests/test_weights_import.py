@@ -120,3 +120,12 @@ def test_import_cli_with_explicit_map(built_lib, tmp_path):
     assert K2 == K
     for name, (w, b) in ref.items():
         assert (t[name + ".weight"] == w).all() and (t[name + ".bias"] == b).all()
+
+
+def test_import_cli_lists_expected_layers(built_lib):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "import_weights.py"), "--list", "--K", "4"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    specs = arch.conv_specs(4)
+    assert len(lines) == len(specs)
+    assert lines[0] == "backbone.firstconv.0 32x3x3x3" and lines[-1].startswith("head.refine.3.conv_out 1x32x3x3")
