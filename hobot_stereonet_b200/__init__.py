@@ -5,4 +5,4 @@ Only the hot path lives here: `csrc/` (sm_100a kernels + C ABI, built into lib/l
 node's interface).  Nothing in this package imports `oracle/`.
 """
 from . import capi  # noqa: F401
-from .capi import Model, SnbError  # noqa: F401
+from .capi import Model, Pool, SnbError  # noqa: F401

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsnb200.so")
 
 SNB_OK, SNB_ERR_INVALID, SNB_ERR_MODEL, SNB_ERR_CUDA, SNB_ERR_NOMEM, SNB_ERR_BUSY = 0, -1, -2, -3, -4, -5
 PREC_FP32, PREC_TC_F16X2 = 0, 1
+FLAG_DEFER_WEIGHTS = 1024
 FLAG_KEEP_STAGES, FLAG_NO_GRAPH, FLAG_CORRECT_CHROMA, FLAG_NO_TENSOR, FLAG_NO_FUSE, FLAG_NO_STREAM, FLAG_PIPE, FLAG_NO_HBMCONV, FLAG_NO_COALESCE, FLAG_PAIR = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
 LAYOUT_NCHW, TENSOR_S8, TENSOR_S32 = 2, 1, 3
 
@@ -36,6 +37,11 @@ class SnbRtStat(C.Structure):
     _fields_ = [("input_fps", C.c_float), ("output_fps", C.c_float), ("infer_time_ms", C.c_int32),
                 ("fps_updated", C.c_int32), ("gpu_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("kernel_launches", C.c_int32)]
+
+
+class SnbPoolStat(C.Structure):
+    _fields_ = [("n_devices", C.c_int32), ("device", C.c_int32 * 16), ("calls", C.c_int64 * 16), ("weight_bytes", C.c_uint64),
+                ("broadcast_ms", C.c_float)]
 
 
 class SnbKernelTime(C.Structure):
@@ -78,6 +84,22 @@ def load() -> C.CDLL:
         "snb_post_parse_depth": (C.c_int, [vp, i64, C.c_float, vp]),
         "snb_weights_synthesize": (i64, [i32, u64, vp, u64]),
         "snb_post_depth_color": (C.c_int, [vp, vp, i32, C.c_float, vp, vp, i32]),
+        "snb_infer_nv12_async": (C.c_int, [vp, vp, vp, i32, DONE_FN, vp, i32]),
+        "snb_pre_nv12_gpu": (C.c_int, [vp, vp, i32, vp]),
+        "snb_pre_nv12_to_bgr": (C.c_int, [vp, i32, i32, vp]),
+        "snb_jpeg_encode_nv12": (i64, [vp, i32, i32, i32, vp, u64]),
+        "snb_weights_validate": (C.c_int, [vp, u64, i32]),
+        "snb_shard_range": (C.c_int, [i64, i32, i32, C.POINTER(i64), C.POINTER(i64)]),
+        "snb_pool_create": (C.c_int, [C.POINTER(vp), C.POINTER(SnbConfig), C.POINTER(i32), i32]),
+        "snb_pool_destroy": (None, [vp]),
+        "snb_pool_size": (i32, [vp]),
+        "snb_pool_ctx": (vp, [vp, i32]),
+        "snb_pool_infer_async": (C.c_int, [vp, vp, vp, i32, DONE_FN, vp, i32]),
+        "snb_pool_infer_nv12_async": (C.c_int, [vp, vp, vp, i32, DONE_FN, vp, i32]),
+        "snb_pool_infer": (C.c_int, [vp, vp, vp, i32]),
+        "snb_pool_wait_all": (C.c_int, [vp]),
+        "snb_pool_get_stat": (C.c_int, [vp, C.POINTER(SnbPoolStat)]),
+        "snb_pool_last_error": (C.c_char_p, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -181,7 +203,14 @@ class Model:
     def infer_device(self, d_in, d_out, batch: int, stream: int = 0):
         self._check(self._l.snb_infer_device(self._h, _ptr(d_in), _ptr(d_out), batch, stream or None))
 
-    def infer_async(self, s8, out, done=None, timeout_ms: int = -1):
+    def pre_nv12_gpu(self, frames) -> np.ndarray:
+        """CvtNV12Data2Tensors on the GPU: uint8 [B, H*3/2, 2W] frames -> the int8 [B,6,H,W] tensor (host)."""
+        B = frames.shape[0]
+        out = np.empty((B, 6, self.H, self.W), np.int8)
+        self._check(self._l.snb_pre_nv12_gpu(self._h, _ptr(frames), B, _ptr(out)))
+        return out
+
+    def infer_async(self, s8, out, done=None, timeout_ms: int = -1, nv12: bool = False):
         key = id(out)
 
         def _cb(user, status, stat):
@@ -194,10 +223,15 @@ class Model:
 
         cb = DONE_FN(_cb)
         self._cbs[key] = (cb, s8, out)      # keep buffers and the thunk alive until the callback fired
-        r = self._l.snb_infer_async(self._h, _ptr(s8), _ptr(out), s8.shape[0], cb, None, timeout_ms)
+        fn = self._l.snb_infer_nv12_async if nv12 else self._l.snb_infer_async
+        r = fn(self._h, _ptr(s8), _ptr(out), s8.shape[0], cb, None, timeout_ms)
         if r < 0:
             self._cbs.pop(key, None)
             self._check(r)
+
+    def infer_nv12_async(self, frames, out, done=None, timeout_ms: int = -1):
+        """frames: uint8 [B, H*3/2, 2W] raw camera frames (host, ideally pinned); the pre-process runs inside the pass."""
+        self.infer_async(frames, out, done, timeout_ms, nv12=True)
 
     def wait_all(self):
         self._check(self._l.snb_wait_all(self._h))
@@ -231,6 +265,111 @@ class Model:
         arr = (SnbKernelTime * 512)()
         n = self._check(self._l.snb_profile_pass(self._h, batch, arr, 512))
         return [(arr[i].name.decode(), arr[i].ms, arr[i].flops, arr[i].bytes) for i in range(n)]
+
+
+class Pool:
+    """One model replica per GPU behind one handle (snb_pool_*): replica 0 loads the weights, one NCCL broadcast installs
+    them on the other GPUs, calls go to the least busy replica, batches are sharded contiguously."""
+
+    def __init__(self, height: int, width: int, K: int, D: int, *, devices=None, max_batch: int = 1, task_num: int = 4,
+                 precision: int = PREC_TC_F16X2, flags: int = 0, model_file: Optional[str] = None, weights: Optional[bytes] = None):
+        self._l = lib()
+        self._h = C.c_void_p()
+        self._cbs = {}
+        cfg = SnbConfig(C.sizeof(SnbConfig), height, width, K, D, max_batch, 0, task_num, precision, flags,
+                        model_file.encode() if model_file else None, None, 0)
+        self._wbuf = None
+        if weights is not None:
+            self._wbuf = C.create_string_buffer(weights, len(weights))
+            cfg.weights = C.cast(self._wbuf, C.c_void_p)
+            cfg.weights_bytes = len(weights)
+        devs = (C.c_int32 * len(devices))(*devices) if devices else None
+        r = self._l.snb_pool_create(C.byref(self._h), C.byref(cfg), devs, len(devices) if devices else 0)
+        if r != SNB_OK:
+            raise SnbError(r, (self._l.snb_pool_last_error(None) or b"").decode())
+        self.H, self.W, self.K, self.D = height, width, K, D
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._l.snb_pool_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def _check(self, r: int):
+        if r < 0:
+            raise SnbError(r, (self._l.snb_pool_last_error(self._h) or b"").decode())
+        return r
+
+    def size(self) -> int:
+        return int(self._l.snb_pool_size(self._h))
+
+    def infer(self, s8, out=None):
+        B = s8.shape[0]
+        if out is None:
+            out = np.empty((B, 1, self.H, self.W), np.int32)
+        self._check(self._l.snb_pool_infer(self._h, _ptr(s8), _ptr(out), B))
+        return out
+
+    def infer_async(self, x, out, nv12: bool = False, timeout_ms: int = -1):
+        key = id(out)
+
+        def _cb(user, status, stat):
+            self._cbs.pop(key, None)
+
+        cb = DONE_FN(_cb)
+        self._cbs[key] = (cb, x, out)
+        fn = self._l.snb_pool_infer_nv12_async if nv12 else self._l.snb_pool_infer_async
+        r = fn(self._h, _ptr(x), _ptr(out), x.shape[0], cb, None, timeout_ms)
+        if r < 0:
+            self._cbs.pop(key, None)
+            self._check(r)
+
+    def wait_all(self):
+        self._check(self._l.snb_pool_wait_all(self._h))
+
+    def stat(self) -> dict:
+        s = SnbPoolStat()
+        self._check(self._l.snb_pool_get_stat(self._h, C.byref(s)))
+        n = s.n_devices
+        return {"n_devices": n, "devices": list(s.device[:n]), "calls": list(s.calls[:n]), "weight_bytes": int(s.weight_bytes),
+                "broadcast_ms": float(s.broadcast_ms)}
+
+
+def shard_range(n_pairs: int, world: int, rank: int):
+    a, b = C.c_int64(), C.c_int64()
+    r = lib().snb_shard_range(n_pairs, world, rank, C.byref(a), C.byref(b))
+    if r < 0:
+        raise SnbError(r, "snb_shard_range")
+    return a.value, b.value
+
+
+def weights_validate(blob: bytes, K: int = 0) -> None:
+    """Raises SnbError(SNB_ERR_MODEL, reason) unless `blob` is a weight blob snb_create would accept."""
+    buf = C.create_string_buffer(blob, len(blob))
+    r = lib().snb_weights_validate(C.cast(buf, C.c_void_p), len(blob), K)
+    if r < 0:
+        raise SnbError(r, (lib().snb_last_error(None) or b"").decode())
+
+
+def nv12_to_bgr(nv12: np.ndarray, w: int, h: int) -> np.ndarray:
+    out = np.empty((h, w, 3), np.uint8)
+    r = lib().snb_pre_nv12_to_bgr(_ptr(np.ascontiguousarray(nv12, np.uint8)), w, h, _ptr(out))
+    if r < 0:
+        raise SnbError(r, "snb_pre_nv12_to_bgr")
+    return out
+
+
+def jpeg_encode_nv12(nv12: np.ndarray, w: int, h: int, quality: int = 0) -> bytes:
+    src = np.ascontiguousarray(nv12, np.uint8)
+    n = lib().snb_jpeg_encode_nv12(_ptr(src), w, h, quality, None, 0)
+    if n < 0:
+        raise SnbError(int(n), "snb_jpeg_encode_nv12")
+    dst = np.empty(n, np.uint8)
+    n2 = lib().snb_jpeg_encode_nv12(_ptr(src), w, h, quality, _ptr(dst), n)
+    if n2 != n:
+        raise SnbError(int(n2), "snb_jpeg_encode_nv12")
+    return dst.tobytes()
 
 
 def synthesize_weights(K: int, seed: int = 1234) -> bytes:

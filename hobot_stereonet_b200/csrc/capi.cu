@@ -36,11 +36,37 @@ static int fail(snb_ctx* c, int code, const char* msg) {
 
 static void worker_main(snb_ctx* c);
 
+// one eager pass over zeros: sets kernel attributes outside graph capture and surfaces launch errors at init
+static int warm_up(snb_ctx* c) {
+  cudaMemsetAsync(c->d_in, 0, c->in_bytes * c->maxB, c->stream);
+  launch_pre_s8(c->d_in, c->img, c->maxB, c->H, c->W, c->stream);
+  int r = run_plan(c, c->maxB, c->stream, false);
+  if (r == SNB_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) {
+    snprintf(c->err, sizeof(c->err), "warm-up pass failed: %s", cudaGetErrorString(cudaGetLastError()));
+    r = SNB_ERR_CUDA;
+  }
+  if (r == SNB_OK) c->warmed = true;
+  return r;
+}
+
 extern "C" {
 
 const char* snb_version(void) { return "snb200 0.1 (sm_100a)"; }
 
 const char* snb_last_error(const snb_ctx* ctx) { return ctx ? ctx->err : g_err; }
+
+// Host-only check of a weight blob against the topology for K refinement stages (K <= 0: the K stored in the blob):
+// what snb_create / snb_set_weights would accept.  The message of a rejection is in snb_last_error(NULL).
+int snb_weights_validate(const void* blob, uint64_t bytes, int32_t K) {
+  std::map<std::string, HostTensor> wts;
+  int blob_K = -1;
+  int r = parse_blob(blob, bytes, &wts, &blob_K, g_err, sizeof(g_err));
+  if (r == SNB_OK && K > 0 && blob_K != K) {
+    snprintf(g_err, sizeof(g_err), "weight blob was generated for K=%d, asked K=%d", blob_K, K);
+    r = SNB_ERR_MODEL;
+  }
+  return r;
+}
 
 int snb_create(snb_ctx** out, const snb_config* cfg) {
   if (!out || !cfg || cfg->struct_size != (int32_t)sizeof(snb_config)) return fail(nullptr, SNB_ERR_INVALID, "snb_create: bad config struct");
@@ -53,8 +79,11 @@ int snb_create(snb_ctx** out, const snb_config* cfg) {
     return fail(nullptr, SNB_ERR_INVALID, "snb_create: unknown precision");
 
   // model file check first, as SetNodePara does (stereonet_node.cpp:131-134)
+  const bool defer = (cfg->flags & SNB_FLAG_DEFER_WEIGHTS) != 0;
   std::vector<char> blob;
-  if (cfg->weights && cfg->weights_bytes) {
+  if (defer) {
+    // multi-GPU init (pool.cu): the weights arrive later from another GPU, through snb_set_weights
+  } else if (cfg->weights && cfg->weights_bytes) {
     blob.assign((const char*)cfg->weights, (const char*)cfg->weights + cfg->weights_bytes);
   } else {
     if (!cfg->model_file || access(cfg->model_file, F_OK) != 0) {
@@ -95,10 +124,14 @@ int snb_create(snb_ctx** out, const snb_config* cfg) {
   if (cudaSetDevice(cfg->device) != cudaSuccess) { snprintf(c->err, sizeof(c->err), "cudaSetDevice failed"); return bail(SNB_ERR_CUDA); }
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { snprintf(c->err, sizeof(c->err), "stream create failed"); return bail(SNB_ERR_CUDA); }
   for (auto& e : c->ev) cudaEventCreate(&e);
-  int r = parse_blob(c, blob.data(), blob.size());
-  if (r != SNB_OK) return bail(r);
-  r = upload_weights(c);
-  if (r != SNB_OK) return bail(r);
+  cudaEventCreateWithFlags(&c->ev_last, cudaEventDisableTiming);
+  int r = SNB_OK;
+  if (!defer) {
+    r = parse_blob(blob.data(), blob.size(), &c->wts, &c->blob_K, c->err, sizeof(c->err));
+    if (r != SNB_OK) return bail(r);
+    r = upload_weights(c);
+    if (r != SNB_OK) return bail(r);
+  }
   if (cudaMalloc(&c->d_in, c->in_bytes * c->maxB) != cudaSuccess || cudaMalloc(&c->d_out, c->out_bytes * c->maxB) != cudaSuccess ||
       cudaMalloc(&c->d_frames, c->frame_bytes * c->maxB) != cudaSuccess) {
     snprintf(c->err, sizeof(c->err), "cudaMalloc io staging failed");
@@ -109,24 +142,21 @@ int snb_create(snb_ctx** out, const snb_config* cfg) {
   cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking);
   c->slots.resize(std::max(1, std::min(cfg->task_num, 8)));
   for (auto& sl : c->slots) {
-    if (cudaMalloc(&sl.d_in, c->in_bytes * c->maxB) != cudaSuccess || cudaMalloc(&sl.d_out, c->out_bytes * c->maxB) != cudaSuccess) {
+    if (cudaMalloc(&sl.d_in, c->in_bytes * c->maxB) != cudaSuccess || cudaMalloc(&sl.d_out, c->out_bytes * c->maxB) != cudaSuccess ||
+        cudaMalloc(&sl.d_frames, c->frame_bytes * c->maxB) != cudaSuccess) {
       snprintf(c->err, sizeof(c->err), "cudaMalloc async staging failed");
       return bail(SNB_ERR_NOMEM);
     }
     cudaEventCreate(&sl.e_in); cudaEventCreate(&sl.e_done);
     cudaEventCreateWithFlags(&sl.e_out, cudaEventBlockingSync);
   }
-  r = build_plan(c);
-  if (r != SNB_OK) return bail(r);
-  // one eager warm-up pass: sets kernel attributes outside graph capture and surfaces launch errors now
-  cudaMemsetAsync(c->d_in, 0, c->in_bytes * c->maxB, c->stream);
-  launch_pre_s8(c->d_in, c->img, c->maxB, c->H, c->W, c->stream);
-  r = run_plan(c, c->maxB, c->stream, false);
-  if (r == SNB_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) {
-    snprintf(c->err, sizeof(c->err), "warm-up pass failed: %s", cudaGetErrorString(cudaGetLastError()));
-    r = SNB_ERR_CUDA;
+  if (defer) {
+    c->broken = true;                  // no model yet: every infer call returns SNB_ERR_MODEL until snb_set_weights succeeds
+  } else {
+    r = build_plan(c);
+    if (r == SNB_OK) r = warm_up(c);
+    if (r != SNB_OK) return bail(r);
   }
-  if (r != SNB_OK) return bail(r);
   c->fps_t0 = now_s();
   c->worker = std::thread(worker_main, c);
   *out = c;
@@ -147,25 +177,44 @@ void snb_destroy(snb_ctx* c) {
   delete c;
 }
 
+// Wait until the most recent pass - on whatever stream it was enqueued - has finished.
+static void sync_last_pass(snb_ctx* c) {
+  cudaStreamSynchronize(c->stream);
+  if (c->last_stream) cudaEventSynchronize(c->ev_last);
+}
+
 int snb_set_weights(snb_ctx* c, const void* blob, uint64_t bytes, int is_device) {
   if (!c || !blob || !bytes) return fail(c, SNB_ERR_INVALID, "snb_set_weights: bad arguments");
   std::lock_guard<std::mutex> run(c->run_mu);
   cudaSetDevice(c->cfg.device);
-  cudaStreamSynchronize(c->stream);
   std::vector<char> host;
   if (is_device) {
     host.resize(bytes);
     CK(c, cudaMemcpy(host.data(), blob, bytes, cudaMemcpyDeviceToHost));
     blob = host.data();
   }
-  int r = parse_blob(c, blob, bytes);
-  if (r != SNB_OK) return r;
+  // everything that can be wrong with the blob is found here, before the live model is touched
+  std::map<std::string, HostTensor> wts;
+  int blob_K = -1;
+  int r = parse_blob(blob, bytes, &wts, &blob_K, c->err, sizeof(c->err));
+  if (r == SNB_OK && blob_K != c->K) {
+    snprintf(c->err, sizeof(c->err), "weight blob was generated for K=%d, this context runs K=%d", blob_K, c->K);
+    r = SNB_ERR_MODEL;
+  }
+  if (r != SNB_OK) { snprintf(g_err, sizeof(g_err), "%s", c->err); return r; }     // the old model stays installed
+  sync_last_pass(c);                                   // no pass may still read the buffers replaced below
   // device pointers baked into the plan/graphs change: rebuild both
   for (auto& g : c->graphs) cudaGraphExecDestroy(g.second);
   c->graphs.clear();
+  c->wts = std::move(wts); c->blob_K = blob_K;
   r = upload_weights(c);
-  if (r != SNB_OK) return r;
-  return build_plan(c);
+  if (r == SNB_OK) r = build_plan(c);
+  if (r == SNB_OK && !c->warmed) r = warm_up(c);       // a context created with SNB_FLAG_DEFER_WEIGHTS runs its first pass here
+  // only a device allocation can fail at this point: the old plan is gone, so the context refuses to run until a later
+  // snb_set_weights succeeds
+  c->broken = r != SNB_OK;
+  if (r != SNB_OK) snprintf(g_err, sizeof(g_err), "%s", c->err);
+  return r;
 }
 
 // Host tensor memory.  A small header in front of the block records which allocator owns it.
@@ -221,6 +270,12 @@ int snb_get_model_input_size(const snb_ctx* c, int32_t idx, int32_t* w, int32_t*
 // one chunk (<= maxB pairs) on stream st; inputs already in c->d_in / c->img as selected by `src`
 static int run_chunk(snb_ctx* c, int B, const int8_t* d_in, const uint8_t* d_frames, int32_t* d_out, cudaStream_t st) {
   cudaError_t e;
+  if (c->broken) { snprintf(c->err, sizeof(c->err), "no model installed: the last snb_set_weights failed"); return SNB_ERR_MODEL; }
+  // the scratch set is shared by every pass: order this pass behind the previous one when that ran on another stream
+  if (c->last_stream && c->last_stream != st && cudaStreamWaitEvent(st, c->ev_last, 0) != cudaSuccess) {
+    snprintf(c->err, sizeof(c->err), "cudaStreamWaitEvent: %s", cudaGetErrorString(cudaGetLastError()));
+    return SNB_ERR_CUDA;
+  }
   if (d_frames)
     e = launch_pre_nv12(d_frames, c->img, nullptr, B, c->H, c->W, (c->cfg.flags & SNB_FLAG_CORRECT_CHROMA) ? 1 : 0, st);
   else
@@ -231,6 +286,8 @@ static int run_chunk(snb_ctx* c, int B, const int8_t* d_in, const uint8_t* d_fra
   Plane d = c->disp_final; d.n = B;
   e = launch_post_quant(d, d_out, c->H, c->W, c->qmul, st);
   if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "post: %s", cudaGetErrorString(e)); return SNB_ERR_CUDA; }
+  cudaEventRecord(c->ev_last, st);
+  c->last_stream = st;
   c->last_B = B;
   ++c->n_passes;
   return SNB_OK;
@@ -291,25 +348,56 @@ int snb_infer_device(snb_ctx* c, const int8_t* d_in, int32_t* d_out, int32_t bat
   return SNB_OK;
 }
 
-int snb_infer_async(snb_ctx* c, const int8_t* in, int32_t* out, int32_t batch, snb_done_fn done, void* user, int32_t timeout_ms) {
-  if (!c || !in || !out || batch < 1) return fail(c, SNB_ERR_INVALID, "snb_infer_async: bad arguments");
+static int submit_async(snb_ctx* c, const int8_t* in, const uint8_t* frames, int32_t* out, int32_t batch, snb_done_fn done, void* user,
+                        int32_t timeout_ms) {
   std::unique_lock<std::mutex> lk(c->mu);
   const int cap = std::max(1, c->cfg.task_num);
   auto room = [&] { return c->stop || c->inflight < cap; };
   if (timeout_ms < 0) c->cv_push.wait(lk, room);
   else if (!c->cv_push.wait_for(lk, std::chrono::milliseconds(timeout_ms), room)) return fail(c, SNB_ERR_BUSY, "snb_infer_async: no free task slot");
   if (c->stop) return SNB_ERR_INVALID;
-  c->queue.push_back(Task{in, out, batch, done, user});
+  c->queue.push_back(Task{in, frames, out, batch, done, user});
   ++c->inflight;
   lk.unlock();
   c->cv_pop.notify_one();
   return SNB_OK;
 }
 
+int snb_infer_async(snb_ctx* c, const int8_t* in, int32_t* out, int32_t batch, snb_done_fn done, void* user, int32_t timeout_ms) {
+  if (!c || !in || !out || batch < 1) return fail(c, SNB_ERR_INVALID, "snb_infer_async: bad arguments");
+  return submit_async(c, in, nullptr, out, batch, done, user, timeout_ms);
+}
+
+int snb_infer_nv12_async(snb_ctx* c, const uint8_t* frames, int32_t* out, int32_t batch, snb_done_fn done, void* user, int32_t timeout_ms) {
+  if (!c || !frames || !out || batch < 1) return fail(c, SNB_ERR_INVALID, "snb_infer_nv12_async: bad arguments");
+  if ((c->H & 1) || (c->W & 1)) return fail(c, SNB_ERR_INVALID, "snb_infer_nv12_async: NV12 frames need even height and width");
+  return submit_async(c, nullptr, frames, out, batch, done, user, timeout_ms);
+}
+
+// preprocess.cpp:913-1059 on the GPU: the s8 tensor CvtNV12Data2Tensors builds, from raw camera frames
+int snb_pre_nv12_gpu(snb_ctx* c, const uint8_t* frames, int32_t batch, int8_t* s8_out) {
+  if (!c || !frames || !s8_out || batch < 1) return fail(c, SNB_ERR_INVALID, "snb_pre_nv12_gpu: bad arguments");
+  if ((c->H & 1) || (c->W & 1)) return fail(c, SNB_ERR_INVALID, "snb_pre_nv12_gpu: NV12 frames need even height and width");
+  std::lock_guard<std::mutex> run(c->run_mu);
+  if (c->broken) return fail(c, SNB_ERR_MODEL, "no model installed");
+  CK(c, cudaSetDevice(c->cfg.device));
+  sync_last_pass(c);
+  cudaStream_t st = c->stream;
+  for (int b0 = 0; b0 < batch; b0 += c->maxB) {
+    const int B = std::min(c->maxB, batch - b0);
+    CK(c, cudaMemcpyAsync(c->d_frames, frames + (size_t)b0 * c->frame_bytes, c->frame_bytes * B, cudaMemcpyHostToDevice, st));
+    cudaError_t e = launch_pre_nv12(c->d_frames, c->img, c->d_in, B, c->H, c->W, (c->cfg.flags & SNB_FLAG_CORRECT_CHROMA) ? 1 : 0, st);
+    if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "pre_nv12: %s", cudaGetErrorString(e)); return SNB_ERR_CUDA; }
+    CK(c, cudaMemcpyAsync(s8_out + (size_t)b0 * c->in_bytes, c->d_in, c->in_bytes * B, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+  }
+  return SNB_OK;
+}
+
 int snb_wait_all(snb_ctx* c) {
   if (!c) return SNB_ERR_INVALID;
   std::unique_lock<std::mutex> lk(c->mu);
-  c->cv_push.wait(lk, [&] { return c->inflight == 0 || c->stop; });
+  c->cv_push.wait(lk, [&] { return (c->inflight == 0 && c->in_callbacks == 0) || c->stop; });
   return SNB_OK;
 }
 
@@ -328,7 +416,7 @@ int64_t snb_debug_read(snb_ctx* c, const char* name, float* dst, uint64_t cap, i
   if (it == c->stages.end()) return fail(c, SNB_ERR_INVALID, "snb_debug_read: unknown stage");
   std::lock_guard<std::mutex> run(c->run_mu);
   cudaSetDevice(c->cfg.device);
-  cudaStreamSynchronize(c->stream);
+  sync_last_pass(c);
   const Stage& s = it->second;
   const int B = std::max(1, c->last_B);
   if (s.is_plane) {
@@ -412,6 +500,7 @@ int snb_post_depth_color(snb_ctx* c, const int32_t* q, int32_t batch, float alph
 int snb_profile_pass(snb_ctx* c, int32_t batch, snb_kernel_time* out, int32_t cap) {
   if (!c || batch < 1 || batch > c->maxB) return fail(c, SNB_ERR_INVALID, "snb_profile_pass: bad batch");
   std::lock_guard<std::mutex> run(c->run_mu);
+  if (c->broken) return fail(c, SNB_ERR_MODEL, "no model installed");
   CK(c, cudaSetDevice(c->cfg.device));
   cudaStream_t st = c->stream;
   const int n = (int)c->ops.size() + 2;
@@ -470,15 +559,24 @@ static void retire_oldest(snb_ctx* c) {
     }
     st = c->stat;
   }
-  for (const Task& t : sl.tasks)
-    if (t.done) t.done(t.user, status, &st);
-  const int n = (int)sl.tasks.size();
-  sl.tasks.clear();
+  // The pass is over: its staging slot and its task slots are free again BEFORE the callbacks run, so a callback may
+  // submit the next frame (snb_infer_async with timeout -1) without deadlocking on a full task table.  snb_wait_all
+  // counts callbacks still running through `in_callbacks`.
+  std::vector<Task> tasks;
+  tasks.swap(sl.tasks);
   sl.busy = false;
   ++c->n_ret;
   {
     std::unique_lock<std::mutex> lk(c->mu);
-    c->inflight -= n;
+    c->inflight -= (int)tasks.size();
+    c->in_callbacks += (int)tasks.size();
+  }
+  c->cv_push.notify_all();
+  for (const Task& t : tasks)
+    if (t.done) t.done(t.user, status, &st);
+  {
+    std::unique_lock<std::mutex> lk(c->mu);
+    c->in_callbacks -= (int)tasks.size();
   }
   c->cv_push.notify_all();
 }
@@ -491,14 +589,16 @@ static int enqueue_async(snb_ctx* c, const std::vector<Task>& group) {
   CK(c, cudaSetDevice(c->cfg.device));
   sl.tasks = group; sl.t0 = now_s();
   int B = 0;
+  const bool nv12 = group[0].frames != nullptr;        // a pass is fed by ONE pre-process kernel: the worker never mixes kinds
   for (const Task& t : group) {
-    CK(c, cudaMemcpyAsync(sl.d_in + (size_t)B * c->in_bytes, t.in, c->in_bytes * t.batch, cudaMemcpyHostToDevice, c->st_in));
+    if (nv12) CK(c, cudaMemcpyAsync(sl.d_frames + (size_t)B * c->frame_bytes, t.frames, c->frame_bytes * t.batch, cudaMemcpyHostToDevice, c->st_in));
+    else CK(c, cudaMemcpyAsync(sl.d_in + (size_t)B * c->in_bytes, t.in, c->in_bytes * t.batch, cudaMemcpyHostToDevice, c->st_in));
     B += t.batch;
   }
   sl.batch = B;
   CK(c, cudaEventRecord(sl.e_in, c->st_in));
   CK(c, cudaStreamWaitEvent(c->stream, sl.e_in, 0));
-  int r = run_chunk(c, B, sl.d_in, nullptr, sl.d_out, c->stream);
+  int r = run_chunk(c, B, sl.d_in, nv12 ? sl.d_frames : nullptr, sl.d_out, c->stream);
   if (r != SNB_OK) return r;
   CK(c, cudaEventRecord(sl.e_done, c->stream));
   CK(c, cudaStreamWaitEvent(c->st_out, sl.e_done, 0));
@@ -552,7 +652,8 @@ static void worker_main(snb_ctx* c) {
         const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(200);
         std::unique_lock<std::mutex> lk(c->mu);
         for (;;) {
-          while (!c->queue.empty() && total + c->queue.front().batch <= c->maxB) {
+          while (!c->queue.empty() && total + c->queue.front().batch <= c->maxB &&
+                 (c->queue.front().frames != nullptr) == (group[0].frames != nullptr)) {
             group.push_back(c->queue.front()); total += c->queue.front().batch; c->queue.pop_front();
           }
           // stop gathering: the pass is full, the next call does not fit, the caller cannot submit more (every task
@@ -565,7 +666,7 @@ static void worker_main(snb_ctx* c) {
       if (r == SNB_OK) continue;
     } else {
       while (c->n_enq != c->n_ret) retire_oldest(c);   // larger than one pass: chunked synchronous path
-      r = infer_host(c, group[0].in, nullptr, group[0].out, group[0].batch);
+      r = infer_host(c, group[0].in, group[0].frames, group[0].out, group[0].batch);
     }
     snb_rt_stat st = c->stat;
     for (const Task& t : group)

@@ -9,6 +9,7 @@
 #include <algorithm>
 
 #include "kernels.cuh"
+#include "layers.h"
 
 namespace snb {
 
@@ -19,36 +20,69 @@ static const int REF_DIL[6] = {1, 2, 4, 8, 1, 1};
 static const int PAD_BACKBONE = 2, PAD_REFINE = 16;   // the fused residual block reads a 2*dilation halo
 
 // ---- weight blob ("SNB2WGT1", oracle/weights.py documents the layout) -----------------------------
-int parse_blob(snb_ctx* c, const void* blob, size_t bytes) {
+// The blob named by `model_file` is untrusted input: every offset and size is range-checked without overflow, every
+// tensor's byte count must equal 4 * prod(dims), and the table must hold exactly the convolutions of the topology
+// build_plan assumes (layers.h), with those shapes.  Nothing of the context is touched: the result goes to `out`.
+int parse_blob(const void* blob, size_t bytes, std::map<std::string, HostTensor>* out, int* blob_K, char* err, size_t errlen) {
   const uint8_t* p = static_cast<const uint8_t*>(blob);
-  if (bytes < 24 || memcmp(p, "SNB2WGT1", 8) != 0) {
-    snprintf(c->err, sizeof(c->err), "model_file is not a SNB2WGT1 weight blob");
+  if (!p || bytes < 24 || memcmp(p, "SNB2WGT1", 8) != 0) {
+    snprintf(err, errlen, "model_file is not a SNB2WGT1 weight blob");
     return SNB_ERR_MODEL;
   }
   uint32_t ver, K, n;
   memcpy(&ver, p + 8, 4); memcpy(&K, p + 12, 4); memcpy(&n, p + 16, 4);
-  if (ver != 1 || bytes < 24 + (size_t)n * 104) {
-    snprintf(c->err, sizeof(c->err), "weight blob: bad version or truncated table");
+  if (ver != 1 || K < 1 || K > 5 || n > 4096 || bytes < 24 + (size_t)n * 104) {
+    snprintf(err, errlen, "weight blob: bad version / K or truncated table");
     return SNB_ERR_MODEL;
   }
   const size_t base = (24 + (size_t)n * 104 + 63) / 64 * 64;
-  c->wts.clear();
+  if (base > bytes) { snprintf(err, errlen, "weight blob: truncated before the data section"); return SNB_ERR_MODEL; }
+  const size_t avail = bytes - base;
+  std::map<std::string, HostTensor> wts;
   for (uint32_t i = 0; i < n; ++i) {
     const uint8_t* e = p + 24 + (size_t)i * 104;
     char name[65]; memcpy(name, e, 64); name[64] = 0;
     uint32_t ndim, dims[5]; uint64_t off, nb;
     memcpy(&ndim, e + 64, 4); memcpy(dims, e + 68, 20); memcpy(&off, e + 88, 8); memcpy(&nb, e + 96, 8);
-    if (ndim > 5 || base + off + nb > bytes) {
-      snprintf(c->err, sizeof(c->err), "weight blob: tensor %s out of range", name);
+    if (off > avail || nb > avail - off) {
+      snprintf(err, errlen, "weight blob: tensor %s out of range", name);
+      return SNB_ERR_MODEL;
+    }
+    uint64_t cnt = 1;
+    bool ok = ndim == 1 || ndim == 4 || ndim == 5;
+    for (uint32_t k = 0; ok && k < ndim; ++k) {
+      if (dims[k] == 0 || dims[k] > 65536) ok = false;
+      else cnt *= dims[k];
+      if (cnt > ((uint64_t)1 << 32)) ok = false;
+    }
+    if (!ok || nb != cnt * 4) {
+      snprintf(err, errlen, "weight blob: tensor %s has a bad shape or byte count", name);
       return SNB_ERR_MODEL;
     }
     HostTensor t;
     for (uint32_t k = 0; k < ndim; ++k) t.shape.push_back((int)dims[k]);
-    t.data.resize(nb / 4);
+    t.data.resize(cnt);
     memcpy(t.data.data(), p + base + off, nb);
-    c->wts[name] = std::move(t);
+    wts[name] = std::move(t);
   }
-  c->blob_K = (int)K;
+  // the topology build_plan assumes: every convolution present, with these shapes
+  for (const Spec& sp : conv_specs((int)K)) {
+    auto wi = wts.find(sp.name + ".weight"), bi = wts.find(sp.name + ".bias");
+    if (wi == wts.end() || bi == wts.end()) {
+      snprintf(err, errlen, "weight blob lacks %s", sp.name.c_str());
+      return SNB_ERR_MODEL;
+    }
+    std::vector<int> want = {sp.cout, sp.cin};
+    if (sp.kd) want.push_back(sp.kd);
+    want.push_back(sp.ks); want.push_back(sp.ks);
+    if (wi->second.shape != want || bi->second.shape != std::vector<int>{sp.cout}) {
+      snprintf(err, errlen, "weight blob: %s does not have the shape of the network (Cout %d, Cin %d, k %d%s)", sp.name.c_str(),
+               sp.cout, sp.cin, sp.ks, sp.kd ? ", 3-D" : "");
+      return SNB_ERR_MODEL;
+    }
+  }
+  *out = std::move(wts);
+  *blob_K = (int)K;
   return SNB_OK;
 }
 
@@ -104,13 +138,8 @@ int upload_weights(snb_ctx* c) {
     snprintf(c->err, sizeof(c->err), "weight blob was generated for K=%d, config asks K=%d", c->blob_K, c->K);
     return SNB_ERR_MODEL;
   }
-  std::vector<std::string> names;
-  for (auto& kv : c->wts) {
-    const std::string& n = kv.first;
-    if (n.size() > 7 && n.compare(n.size() - 7, 7, ".weight") == 0) names.push_back(n.substr(0, n.size() - 7));
-  }
-  for (auto& n : names) {
-    int r = pack_conv(c, n);
+  for (const Spec& sp : conv_specs(c->K)) {
+    int r = pack_conv(c, sp.name);
     if (r != SNB_OK) return r;
   }
   if (cudaDeviceSynchronize() != cudaSuccess) return SNB_ERR_CUDA;
@@ -637,6 +666,7 @@ void free_ctx(snb_ctx* c) {
   c->wallocs.clear();
   for (auto& sl : c->slots) {
     if (sl.d_in) cudaFree(sl.d_in);
+    if (sl.d_frames) cudaFree(sl.d_frames);
     if (sl.d_out) cudaFree(sl.d_out);
     if (sl.e_in) cudaEventDestroy(sl.e_in);
     if (sl.e_done) cudaEventDestroy(sl.e_done);
@@ -649,6 +679,7 @@ void free_ctx(snb_ctx* c) {
   if (c->d_out) cudaFree(c->d_out);
   if (c->d_frames) cudaFree(c->d_frames);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+  if (c->ev_last) cudaEventDestroy(c->ev_last);
   if (c->stream) cudaStreamDestroy(c->stream);
 }
 

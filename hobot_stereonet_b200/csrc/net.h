@@ -54,13 +54,16 @@ struct Arena {
 };
 
 struct Task {
-  const int8_t* in; int32_t* out; int batch; snb_done_fn done; void* user;
+  const int8_t* in;        // s8 tensor [batch,6,H,W] (host) ...
+  const uint8_t* frames;   // ... or raw side-by-side NV12 frames [batch][H*3/2][2W] (host); exactly one of the two is set
+  int32_t* out; int batch; snb_done_fn done; void* user;
 };
 
 // One in-flight asynchronous pass: its own device staging buffers, so the host->device copy of pass k+1 and the
 // device->host copy of pass k-1 overlap the kernels of pass k (three streams, ordered by events).
 struct AsyncSlot {
   int8_t* d_in = nullptr;
+  uint8_t* d_frames = nullptr;         // NV12 staging of snb_infer_nv12_async passes
   int32_t* d_out = nullptr;
   cudaEvent_t e_in = nullptr, e_done = nullptr, e_out = nullptr;
   std::vector<Task> tasks;             // the calls this pass serves (> 1: coalesced, see worker_main)
@@ -81,6 +84,12 @@ struct snb_ctx {
   int n_tc_convs = 0, n_direct_convs = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // Every pass uses the same scratch (image tensor, arena, graphs): a pass enqueued on one stream must not start before
+  // the previous pass - possibly on another stream (snb_infer_device with a caller's stream) - has finished.
+  cudaEvent_t ev_last = nullptr;       // recorded after the last kernel of the most recent pass
+  cudaStream_t last_stream = nullptr;  // the stream it was recorded on (nullptr: no pass yet)
+  bool warmed = false;                 // the eager warm-up pass has run (kernel attributes set outside graph capture)
+  bool broken = false;                 // a failed snb_set_weights left no usable plan: every infer call returns SNB_ERR_MODEL
 
   int blob_K = -1;
   std::map<std::string, snb::HostTensor> wts;
@@ -110,6 +119,7 @@ struct snb_ctx {
   std::condition_variable cv_push, cv_pop;
   std::deque<snb::Task> queue;
   int inflight = 0;
+  int in_callbacks = 0;                // done-callbacks currently running on the worker thread (snb_wait_all waits for them too)
   bool stop = false;
 
   snb_rt_stat stat{};
@@ -118,7 +128,7 @@ struct snb_ctx {
 };
 
 namespace snb {
-int parse_blob(snb_ctx* c, const void* blob, size_t bytes);
+int parse_blob(const void* blob, size_t bytes, std::map<std::string, HostTensor>* out, int* blob_K, char* err, size_t errlen);
 int upload_weights(snb_ctx* c);
 int build_plan(snb_ctx* c);
 int run_plan(snb_ctx* c, int B, cudaStream_t st, bool use_graph);

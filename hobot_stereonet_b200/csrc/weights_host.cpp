@@ -11,10 +11,9 @@
 #include <vector>
 
 #include "../../include/snb200.h"
+#include "layers.h"
 
-namespace {
-
-struct Spec { std::string name; int cout, cin, kd, ks; float gain; };
+namespace snb {
 
 std::vector<Spec> conv_specs(int K) {
   std::vector<Spec> v;
@@ -48,6 +47,13 @@ std::vector<Spec> conv_specs(int K) {
   }
   return v;
 }
+
+}  // namespace snb
+
+namespace {
+
+using snb::Spec;
+using snb::conv_specs;
 
 struct Rng {
   uint64_t s;

@@ -11,6 +11,7 @@
 #pragma once
 #include <stdint.h>
 
+#include <atomic>
 #include <memory>
 #include <string>
 #include <vector>
@@ -79,6 +80,7 @@ struct DnnNodePara {
   // carries K only, so the instance shape is a parameter here.  Defaults = the deployed model.
   int model_in_h = 720, model_in_w = 1280, D = 12, K = 4;
   int device = 0;
+  std::vector<int> devices;        // more than one entry: one replica per GPU behind snb_pool_* (weights by one NCCL broadcast)
   int precision = SNB_PREC_TC_F16X2;
 };
 
@@ -113,8 +115,17 @@ class DnnNode {
   // the wait for a free task, -1 = forever).  <0 on failure.
   int Run(std::vector<std::shared_ptr<DNNTensor>>& inputs, const std::shared_ptr<DnnNodeOutput>& output,
           bool is_sync_mode = false, int alloctask_timeout_ms = -1, int infer_timeout_ms = -1);
+  // The B200 form of the same call: inputs[0] holds ONE raw side-by-side NV12 camera frame ([H*3/2][2W] bytes) instead of
+  // the s8 tensor; the L/R split, chroma step and x-128 (stereonet_node.cpp:702-738, preprocess.cpp:913-1059) run on the GPU
+  // inside the pass and the upload is half the bytes.  Same output, same callback, same error convention.
+  int RunNv12(std::vector<std::shared_ptr<DNNTensor>>& inputs, const std::shared_ptr<DnnNodeOutput>& output,
+              bool is_sync_mode = false, int alloctask_timeout_ms = -1);
   // Blocks until every enqueued Run has been post-processed (the reference relies on rclcpp::spin).
   int WaitAll();
+  // Drains the in-flight calls (their PostProcess still runs) and releases the GPU side.  A derived class MUST call this
+  // from its own destructor: once ~DnnNode runs, the derived part - and with it PostProcess - is gone.
+  void Shutdown();
+  int device_count() const;
   const std::string& node_name() const { return node_name_; }
   std::string LastError() const;
 
@@ -127,12 +138,20 @@ class DnnNode {
   struct Task;
   static void OnDone(void* user, int status, const snb_rt_stat* stat);
   std::shared_ptr<DNNTensor> AllocOutput();
+  int Submit(std::vector<std::shared_ptr<DNNTensor>>& inputs, const std::shared_ptr<DnnNodeOutput>& output, bool nv12,
+             bool is_sync_mode, int alloctask_timeout_ms);
   std::string node_name_;
   Model model_;
+  std::atomic<bool> derived_gone_{false};   // set by ~DnnNode: results of calls still in flight are dropped, PostProcess is not called
+  snb_pool* pool_ = nullptr;       // set when the node drives more than one GPU; model_.ctx_ is then replica 0
 };
 
-// hbSysAllocCachedMem / hbSysFreeMem (preprocess.cpp:956-960,972)
+// hbSysAllocCachedMem / hbSysFreeMem (preprocess.cpp:956-960,972).  The reference allocates and frees BPU memory per
+// frame; page-locked host memory is expensive to map and its release synchronises the device, so blocks are recycled
+// through a process-wide pool keyed by size (at most kPoolBlocksPerSize idle blocks per size).
+constexpr int kPoolBlocksPerSize = 16;
 std::shared_ptr<DNNTensor> AllocTensor(const hbDNNTensorProperties& props, uint32_t bytes);
+void ReleaseTensorPool();          // frees the idle blocks (tensors still alive free their block when they die)
 
 }  // namespace dnn_node
 }  // namespace hobot

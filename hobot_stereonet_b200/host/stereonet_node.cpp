@@ -2,6 +2,7 @@
 
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <unistd.h>
 
 #include <chrono>
@@ -36,8 +37,21 @@ StereonetNode::StereonetNode(const std::string& node_name, const Params& params)
     return;
   }
   sp_preprocess_ = std::make_shared<PreProcess>("");
+  gpu_preprocess_ = param(params, "preprocess", "gpu") != "cpu" && model_input_width_ % 2 == 0 && model_input_height_ % 2 == 0;
+  jpeg_on_ = param(params, "jpeg", "on") != "off";
+  // the reference's two steps (cv::cvtColor NV12 -> BGR, cv::imencode ".jpg"; stereonet_node.cpp:775-782) restated in the library
+  jpeg_encoder_ = [](const uint8_t* nv12, int w, int h, std::vector<uint8_t>& jpeg) {
+    const int64_t n = snb_jpeg_encode_nv12(nv12, w, h, 0, nullptr, 0);
+    if (n <= 0) return false;
+    jpeg.resize((size_t)n);
+    return snb_jpeg_encode_nv12(nv12, w, h, 0, jpeg.data(), jpeg.size()) == n;
+  };
   ok_ = true;
 }
+
+// In-flight calls complete into PostProcess, which uses this object's publisher and members: drain them while the
+// object is still whole (the base destructor would be too late).
+StereonetNode::~StereonetNode() { Shutdown(); }
 
 int StereonetNode::SetNodePara() {
   if (!dnn_node_para_ptr_) return -1;
@@ -53,6 +67,16 @@ int StereonetNode::SetNodePara() {
   dnn_node_para_ptr_->K = atoi(param(params_, "K", "4").c_str());
   dnn_node_para_ptr_->D = atoi(param(params_, "D", "12").c_str());
   dnn_node_para_ptr_->device = atoi(param(params_, "device", "0").c_str());
+  {
+    const std::string devs = param(params_, "devices", "");
+    size_t pos = 0;
+    while (pos < devs.size()) {
+      size_t end = devs.find(',', pos);
+      if (end == std::string::npos) end = devs.size();
+      if (end > pos) dnn_node_para_ptr_->devices.push_back(atoi(devs.substr(pos, end - pos).c_str()));
+      pos = end + 1;
+    }
+  }
   dnn_node_para_ptr_->precision = param(params_, "precision", "tc") == "fp32" ? SNB_PREC_FP32 : SNB_PREC_TC_F16X2;
   return 0;
 }
@@ -81,26 +105,52 @@ void StereonetNode::FeedImg(const HbmMsg1080P& img_msg) {
   dnn_output->msg_header->stamp_sec = img_msg.time_stamp_sec;
   dnn_output->msg_header->stamp_nanosec = img_msg.time_stamp_nanosec;
 
-  // 3. pre-process: L/R split (:702-738) then CvtNV12Data2Tensors
+  // 3. pre-process.  Reference: L/R split (:702-738) then CvtNV12Data2Tensors, on the host.  Default here: the raw frame
+  //    goes into a (recycled) page-locked tensor and the same bytes are produced on the GPU inside the pass.
   const auto tp_start = std::chrono::steady_clock::now();
-  std::vector<uint8_t> left_buf((size_t)w * h * 3 / 2), right_buf((size_t)w * h * 3 / 2);
-  if (snb_pre_split_nv12(img_msg.data, h, img_msg.width, left_buf.data(), right_buf.data()) != SNB_OK) { ++dropped_; return; }
   std::vector<std::shared_ptr<DNNTensor>> input_tensors;
-  if (sp_preprocess_->CvtNV12Data2Tensors(input_tensors, model_, left_buf.data(), right_buf.data()) < 0) {
-    fprintf(stderr, "[stereonet_node] Preprocess fail\n");
-    ok_ = false;                       // the reference shuts the node down here (:741-744)
-    return;
+  const size_t frame_bytes = (size_t)(h * 3 / 2) * img_msg.width;
+  if (gpu_preprocess_) {
+    hobot::dnn_node::hbDNNTensorProperties props;
+    model_->GetInputTensorProperties(props, 0);
+    auto frame = hobot::dnn_node::AllocTensor(props, (uint32_t)frame_bytes);
+    if (!frame) { ++dropped_; return; }
+    memcpy(frame->sysMem[0].virAddr, img_msg.data, frame_bytes);
+    input_tensors.emplace_back(frame);
+  } else {
+    std::vector<uint8_t> left_buf((size_t)w * h * 3 / 2), right_buf((size_t)w * h * 3 / 2);
+    if (snb_pre_split_nv12(img_msg.data, h, img_msg.width, left_buf.data(), right_buf.data()) != SNB_OK) { ++dropped_; return; }
+    if (sp_preprocess_->CvtNV12Data2Tensors(input_tensors, model_, left_buf.data(), right_buf.data()) < 0) {
+      fprintf(stderr, "[stereonet_node] Preprocess fail\n");
+      ok_ = false;                       // the reference shuts the node down here (:741-744)
+      return;
+    }
   }
   if (enable_pub_output_) {
     auto bin = std::make_shared<BinDataType>();
     bin->w = w; bin->h = h;            // the reference leaves the 1280x720 defaults (stereonet_node.h:43-44)
-    if (jpeg_encoder_ && !jpeg_encoder_(left_buf.data(), w, h, bin->jpeg)) bin->jpeg.clear();
+    if (jpeg_on_ && jpeg_encoder_) {
+      // left view of the side-by-side frame (:752-766), then NV12 -> BGR -> JPEG (:775-782).  The encode does not feed
+      // the model, so it runs beside the GPU pass (at most 4 at once; beyond that the feeding thread does it itself).
+      auto left = std::make_shared<std::vector<uint8_t>>((size_t)w * h * 3 / 2);
+      for (int r = 0; r < h * 3 / 2; ++r) memcpy(left->data() + (size_t)r * w, img_msg.data + (size_t)r * img_msg.width, w);
+      JpegEncoder enc = jpeg_encoder_;
+      auto job = [this, enc, left, w, h]() {
+        std::vector<uint8_t> jpeg;
+        if (!enc(left->data(), w, h, jpeg)) jpeg.clear();
+        --jpeg_inflight_;
+        return jpeg;
+      };
+      const bool spawn = ++jpeg_inflight_ <= 4;
+      bin->jpeg_future = std::async(spawn ? std::launch::async : std::launch::deferred, job).share();
+      if (!spawn) bin->jpeg_future.wait();
+    }
     dnn_output->sp_left_nv12 = bin;
   }
   dnn_output->preprocess_time_ms = now_ms_since(tp_start);
 
   // 4. the hot-path entry (:812): asynchronous, PostProcess fires on the runtime's thread
-  if (Run(input_tensors, dnn_output, false, -1, -1) < 0) {
+  if ((gpu_preprocess_ ? RunNv12(input_tensors, dnn_output, false, -1) : Run(input_tensors, dnn_output, false, -1, -1)) < 0) {
     fprintf(stderr, "[stereonet_node] Run infer fail! %s\n", LastError().c_str());
     return;
   }
@@ -120,6 +170,7 @@ int StereonetNode::PostProcess(const std::shared_ptr<hobot::dnn_node::DnnNodeOut
     msg.encoding = "jpeg";
     msg.header = *out->msg_header;
     const auto& mem = out->output_tensors[0]->sysMem[0];
+    if (out->sp_left_nv12->jpeg_future.valid()) out->sp_left_nv12->jpeg = out->sp_left_nv12->jpeg_future.get();
     const auto& jpeg = out->sp_left_nv12->jpeg;
     msg.data.resize((size_t)mem.memSize + jpeg.size());
     const int64_t n = snb_post_pack(static_cast<const int32_t*>(mem.virAddr), mem.memSize, jpeg.data(), jpeg.size(),

@@ -5,6 +5,7 @@
 // what the publish callback receives; nothing else of the reference's surface changes.
 #pragma once
 #include <functional>
+#include <future>
 #include <map>
 #include <memory>
 #include <string>
@@ -46,6 +47,7 @@ struct BinDataType {                   // stereonet_node.h:40-47
   int w = 1280;
   int h = 720;
   std::vector<uint8_t> jpeg;
+  std::shared_future<std::vector<uint8_t>> jpeg_future;   // the encode runs beside the GPU pass; PostProcess collects it
 };
 
 struct StereonetNodeOutput : public hobot::dnn_node::DnnNodeOutput {   // stereonet_node.h:49-59
@@ -56,8 +58,9 @@ struct StereonetNodeOutput : public hobot::dnn_node::DnnNodeOutput {   // stereo
 
 using Params = std::map<std::string, std::string>;
 // left view as NV12 (w*h*3/2 bytes) -> JPEG bytes.  The reference uses cv::cvtColor + cv::imencode
-// (stereonet_node.cpp:775-782); OpenCV's C++ API is not a dependency of this build, so the encoder
-// is injected.  Without one the JPEG part of the payload is empty.
+// (stereonet_node.cpp:775-782); the default here is the library's own baseline encoder (snb_jpeg_encode_nv12: the same
+// colour conversion bit for bit, quality 95, 4:2:0), so the payload's JPEG half is always present and the untouched render
+// tool can cv2.imdecode it (publisher_member_function.py:93-95).  set_jpeg_encoder replaces it (e.g. by OpenCV's).
 using JpegEncoder = std::function<bool(const uint8_t* nv12, int w, int h, std::vector<uint8_t>& jpeg)>;
 using Publisher = std::function<void(ImageMsg&&)>;
 
@@ -66,7 +69,11 @@ class StereonetNode : public hobot::dnn_node::DnnNode {
   // Parameters (same names and defaults as stereonet_node.cpp:27-35): config_file, model_file,
   // sub_hbmem_topic_name, ros_img_topic_name.  Extra, B200-only: model_in_h, model_in_w, K, D,
   // device, precision ("tc"|"fp32") — the geometry the reference compiles into its .hbm.
+  // More B200-only parameters: devices ("0,1,2,3": one replica per GPU, frames go to the least busy one),
+  // preprocess ("gpu" default: the raw NV12 frame is uploaded and split/converted on the GPU | "cpu": the reference's host
+  // path through PreProcess::CvtNV12Data2Tensors), jpeg ("on" default | "off": empty JPEG part).
   explicit StereonetNode(const std::string& node_name = "stereonet_node", const Params& params = Params());
+  ~StereonetNode() override;
 
   bool ok() const { return ok_; }      // false: "Node init fail!" (the reference calls rclcpp::shutdown())
   void FeedImg(const HbmMsg1080P& img_msg);
@@ -96,6 +103,9 @@ class StereonetNode : public hobot::dnn_node::DnnNode {
   Publisher ros_img_publisher_;
   JpegEncoder jpeg_encoder_;
   bool ok_ = false;
+  bool gpu_preprocess_ = true;
+  bool jpeg_on_ = true;
+  std::atomic<int> jpeg_inflight_{0};
   int dropped_ = 0;
 };
 

@@ -24,7 +24,7 @@ class StereonetRos : public rclcpp::Node {
   StereonetRos() : rclcpp::Node("stereonet_node") {
     hobot::stereonet::Params params;
     for (const auto& kv : defaults_) params[kv.first] = this->declare_parameter<std::string>(kv.first, kv.second);
-    for (const char* k : {"model_in_h", "model_in_w", "K", "D", "device", "precision"}) {
+    for (const char* k : {"model_in_h", "model_in_w", "K", "D", "device", "devices", "precision", "preprocess", "jpeg"}) {
       const std::string v = this->declare_parameter<std::string>(k, "");
       if (!v.empty()) params[k] = v;
     }
@@ -67,9 +67,10 @@ class StereonetRos : public rclcpp::Node {
                                                      {"model_file", "config/hobot_stereonet.snb"},
                                                      {"sub_hbmem_topic_name", "hbmem_stereo_img"},
                                                      {"ros_img_topic_name", "/stereonet_node_output"}};
-  std::unique_ptr<hobot::stereonet::StereonetNode> node_;
   rclcpp::Publisher<sensor_msgs::msg::Image>::SharedPtr pub_;
   rclcpp::Subscription<hbm_img_msgs::msg::HbmMsg1080P>::SharedPtr sub_;
+  // declared last = destroyed first: ~StereonetNode drains the in-flight calls, whose PostProcess publishes through pub_
+  std::unique_ptr<hobot::stereonet::StereonetNode> node_;
 };
 
 }  // namespace

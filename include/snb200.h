@@ -52,6 +52,7 @@ enum {
   SNB_FLAG_NO_HBMCONV = 128,  /* diagnostics: firstconv.0 on the tcgen05 streaming kernel instead of k_conv_first (k_conv_hbm.cu) */
   SNB_FLAG_NO_COALESCE = 256, /* snb_infer_async: one pass per call even when max_batch > 1 (default: queued calls are merged into passes of up to max_batch pairs) */
   SNB_FLAG_PAIR = 512,        /* experiment: 64-channel BasicBlocks as one thread-block-cluster launch with the intermediate rows handed over through distributed shared memory (k_conv_pair.cu; correct, not faster at one pair per pass) */
+  SNB_FLAG_DEFER_WEIGHTS = 1024, /* snb_create without a model: the weights arrive through snb_set_weights (multi-GPU init, snb_pool_create); until then every infer call returns SNB_ERR_MODEL */
   SNB_FLAG_PIPE = 64          /* experiment: layer2's identity blocks as one layer-pipelined launch (k_conv_pipe.cu; correct but slower) */
 };
 
@@ -108,6 +109,11 @@ SNB_API int snb_set_weights(snb_ctx* ctx, const void* blob, uint64_t bytes, int 
  * recoverable from its BPU binary).  dst == NULL: returns the size needed.  Host-only, no GPU. */
 SNB_API int64_t snb_weights_synthesize(int32_t K, uint64_t seed, void* dst, uint64_t cap);
 
+/* Host-only validation of a weight blob (no GPU): magic, table bounds, byte counts, and every convolution of the K-stage
+ * topology present with its shape - exactly what snb_create / snb_set_weights accept.  K <= 0: use the K in the blob.
+ * Returns SNB_OK or SNB_ERR_MODEL (reason: snb_last_error(NULL)). */
+SNB_API int snb_weights_validate(const void* blob, uint64_t bytes, int32_t K);
+
 /* ---- hbSysAllocCachedMem / hbSysFreeMem (preprocess.cpp:956-960,972): host buffers for tensors ----- */
 /* Page-locked host memory when a CUDA device is present (so snb_infer's copies are true async DMA),
  * plain aligned host memory otherwise.  hbSysFlushMem has no equivalent: nothing to flush. */
@@ -138,12 +144,53 @@ SNB_API int snb_infer_device(snb_ctx* ctx, const int8_t* d_in, int32_t* d_out, i
  * frames: batch x side-by-side NV12 [H*3/2, 2W] host memory. */
 SNB_API int snb_infer_nv12(snb_ctx* ctx, const uint8_t* frames, int32_t* out, int32_t batch);
 
+/* The asynchronous form of snb_infer_nv12: the node uploads the raw camera frame (3 bytes per pixel pair position instead of
+ * the 6-plane s8 tensor: half the host->device bytes) and the L/R split, the chroma "444" step and the x-128 of
+ * stereonet_node.cpp:702-738 + preprocess.cpp:913-1059 run on the GPU inside the pass.  Same queue, task slots, callback
+ * thread and merging of queued calls as snb_infer_async (calls of the two kinds are never merged into one pass). */
+SNB_API int snb_infer_nv12_async(snb_ctx* ctx, const uint8_t* frames, int32_t* out, int32_t batch,
+                                 snb_done_fn done, void* user, int32_t timeout_ms);
+/* PreProcess::CvtNV12Data2Tensors (preprocess.cpp:913-1059) on the GPU, as a call of its own: batch side-by-side NV12
+ * frames (host) -> the s8 NCHW [batch,6,H,W] tensor (host), byte-identical to snb_pre_cvt_nv12_to_tensor on the split
+ * views (SNB_FLAG_CORRECT_CHROMA selects the de-interleaving variant). */
+SNB_API int snb_pre_nv12_gpu(snb_ctx* ctx, const uint8_t* frames, int32_t batch, int8_t* s8_out);
+
 /* Whole-network passes launched so far (each = kernel_launches kernels).  With coalescing a pass can serve several
  * snb_infer_async calls, so passes <= calls. */
 SNB_API int64_t snb_get_pass_count(const snb_ctx* ctx);
 SNB_API int snb_get_rt_stat(const snb_ctx* ctx, snb_rt_stat* stat);
 SNB_API const char* snb_last_error(const snb_ctx* ctx);   /* ctx may be NULL: last create error */
 SNB_API const char* snb_version(void);
+
+/* ---- one node process, N GPUs: replicas + batch sharding ------------------------------------------
+ * The reference drives ONE BPU (stereonet_node.cpp:44 Init, :812 Run); a B200 box has eight GPUs.  snb_pool_create makes one
+ * replica of the model per listed device (devices == NULL: every visible GPU; cfg->device is ignored): replica 0 loads
+ * model_file, ONE ncclBroadcast over NVLink puts the blob into every other GPU's memory and each replica installs it from
+ * there (snb_set_weights, is_device = 1).  Nothing is exchanged on the per-frame path.
+ *   snb_pool_infer_async / _nv12_async: one call = one Run(); goes to the replica with the fewest calls in flight.
+ *   snb_pool_infer: a batch in one call; contiguous shards (snb_shard_range), all replicas at once; returns when done. */
+typedef struct snb_pool snb_pool;
+typedef struct snb_pool_stat {
+  int32_t n_devices;
+  int32_t device[16];       /* CUDA ordinals */
+  int64_t calls[16];        /* calls (or shards) served by each replica */
+  uint64_t weight_bytes;    /* size of the broadcast blob */
+  float broadcast_ms;       /* device time of the NCCL broadcast (0 for a pool of one) */
+} snb_pool_stat;
+SNB_API int snb_pool_create(snb_pool** out, const snb_config* cfg, const int32_t* devices, int32_t n_devices);
+SNB_API void snb_pool_destroy(snb_pool* pool);
+SNB_API int32_t snb_pool_size(const snb_pool* pool);
+SNB_API snb_ctx* snb_pool_ctx(const snb_pool* pool, int32_t replica);      /* for snb_get_io, snb_get_rt_stat ... */
+SNB_API int snb_pool_infer_async(snb_pool* pool, const int8_t* in, int32_t* out, int32_t batch,
+                                 snb_done_fn done, void* user, int32_t timeout_ms);
+SNB_API int snb_pool_infer_nv12_async(snb_pool* pool, const uint8_t* frames, int32_t* out, int32_t batch,
+                                      snb_done_fn done, void* user, int32_t timeout_ms);
+SNB_API int snb_pool_infer(snb_pool* pool, const int8_t* in, int32_t* out, int32_t batch);
+SNB_API int snb_pool_wait_all(snb_pool* pool);
+SNB_API int snb_pool_get_stat(const snb_pool* pool, snb_pool_stat* stat);
+SNB_API const char* snb_pool_last_error(const snb_pool* pool);              /* pool may be NULL: last create error */
+/* Contiguous [start, stop) of n_pairs owned by `rank` of `world`, remainder to the lowest ranks (host-only arithmetic). */
+SNB_API int snb_shard_range(int64_t n_pairs, int32_t world, int32_t rank, int64_t* start, int64_t* stop);
 
 /* ---- stage taps for parity tests (needs SNB_FLAG_KEEP_STAGES) ----------------------------------- */
 /* Copies stage `name` of the last pass to host as dense fp32 in [N,C,(D,)H,W] order.
@@ -166,6 +213,13 @@ SNB_API int8_t snb_pre_quantize(float value, float scale, float zero_point, floa
 /* stereonet_node.cpp:1033-1049: payload = s32 output || jpeg; returns bytes written or <0. */
 SNB_API int64_t snb_post_pack(const int32_t* infer, uint64_t infer_bytes, const uint8_t* jpeg, uint64_t jpeg_bytes,
                               uint8_t* dst, uint64_t cap);
+/* stereonet_node.cpp:775-777 cv::cvtColor(nv12, bgr, CV_YUV2BGR_NV12): one NV12 view [h*3/2, w] -> BGR u8 [h, w, 3]
+ * (OpenCV's BT.601 fixed-point formula, bit-exact).  w and h even. */
+SNB_API int snb_pre_nv12_to_bgr(const uint8_t* nv12, int32_t w, int32_t h, uint8_t* bgr);
+/* stereonet_node.cpp:775-782 cvtColor + cv::imencode(".jpg"): baseline JFIF (4:2:0, quality <= 0: OpenCV's default 95)
+ * of one NV12 view, the part of the payload the render tool hands to cv2.imdecode (publisher_member_function.py:93-95).
+ * Returns the JPEG size; nothing is written past cap (dst may be NULL to size the buffer).  Host-only. */
+SNB_API int64_t snb_jpeg_encode_nv12(const uint8_t* nv12, int32_t w, int32_t h, int32_t quality, uint8_t* dst, uint64_t cap);
 /* parser.cpp:79-87 ParseTensor: s32 -> depth in metres (float), f = 527.19..., B = 119.89... mm. */
 SNB_API int snb_post_parse_depth(const int32_t* q, int64_t n, float scale, float* depth_m);
 

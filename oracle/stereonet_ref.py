@@ -35,9 +35,13 @@ def quant_multiplier(cfg: Config) -> np.float32:
 
 class Oracle:
     def __init__(self, cfg: Config, weights: Dict[str, np.ndarray],
-                 round_fn: Optional[Callable[[torch.Tensor, str], torch.Tensor]] = None):
+                 round_fn: Optional[Callable[[torch.Tensor, str], torch.Tensor]] = None,
+                 dtype: torch.dtype = torch.float32):
         self.cfg = cfg
-        self.w: Tensors = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in weights.items()}
+        # dtype = torch.float64 gives the exact-arithmetic value of the same float model (the fp32 weights and inputs are
+        # exactly representable): the yardstick for the rounding noise of the fp32 oracle itself (tests/test_gpu_d192.py)
+        self.dtype = dtype
+        self.w: Tensors = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dtype) for k, v in weights.items()}
         # optional operand rounding for precision studies: round_fn(tensor, tag) -> tensor with
         # tag = "<layer name>:a" (activation operand) / "<layer name>:w" (weight operand) / "costvol",
         # e.g. lambda t, tag: t.half().float() if tag.startswith("head.refine") else t
@@ -107,7 +111,7 @@ class Oracle:
 
     def soft_argmin(self, cost):
         p = torch.softmax(cost, dim=1)
-        d = torch.arange(self.cfg.D, dtype=torch.float32, device=cost.device).view(1, -1, 1, 1) / self.cfg.D
+        d = torch.arange(self.cfg.D, dtype=cost.dtype, device=cost.device).view(1, -1, 1, 1) / self.cfg.D
         return (p * d).sum(1, keepdim=True)                             # [B,1,h,w] in [0,1)
 
     def refine(self, disp, left, s, dump=None):
@@ -130,7 +134,7 @@ class Oracle:
         """s8 [B,6,H,W] int8 -> normalised disparity [B,Hp,Wp] float32 (disp_px / max_disp)."""
         cfg = self.cfg
         assert s8.dtype == np.int8 and s8.shape[1:] == (6, cfg.H, cfg.W), s8.shape
-        return self.forward_float(torch.from_numpy(s8.astype(np.float32)) * IN_SCALE, dump)
+        return self.forward_float((torch.from_numpy(s8.astype(np.float32)) * IN_SCALE).to(self.dtype), dump)
 
     @torch.no_grad()
     def forward_float(self, x: torch.Tensor, dump: Optional[dict] = None) -> torch.Tensor:
@@ -158,11 +162,11 @@ class Oracle:
     def forward_px(self, s8: np.ndarray) -> np.ndarray:
         """Left-view disparity in pixels, cropped to the valid H x W."""
         dn = self.forward_norm(s8).numpy()
-        return dn[:, :self.cfg.H, :self.cfg.W] * np.float32(self.cfg.max_disp)
+        return dn[:, :self.cfg.H, :self.cfg.W] * dn.dtype.type(self.cfg.max_disp)
 
     def forward_s32(self, s8: np.ndarray) -> np.ndarray:
         """The model output tensor as the reference reads it (stereonet_node.cpp:1033):
         int32 NCHW [B,1,H,W], value * OUT_SCALE * 192 = disparity in pixels."""
-        dn = self.forward_norm(s8).numpy()[:, :self.cfg.H, :self.cfg.W]
+        dn = self.forward_norm(s8).numpy()[:, :self.cfg.H, :self.cfg.W].astype(np.float32)
         q = np.rint(dn * quant_multiplier(self.cfg)).astype(np.int32)
         return q[:, None]

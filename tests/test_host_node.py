@@ -72,18 +72,57 @@ def test_cli_payload_matches_binding(built_lib, tmp_path):
     assert f"fed {N} frame(s), published {N}, dropped 0" in r.stderr
     raw = np.frombuffer((tmp_path / "out.bin").read_bytes(), np.uint8)
     m = Model(H, W, K, D, weights=blob, precision=capi.PREC_TC_F16X2)
-    rec = 16 + H * W * 4
-    assert raw.size == N * rec
-    seen = set()
+    pos, seen = 0, set()
     for i in range(N):                       # async: arrival order is the task order (one worker), ids still checked
-        hdr = raw[i * rec:i * rec + 16].view(np.uint32)
-        idx = int(hdr[0]); seen.add(idx)
-        assert (int(hdr[1]), int(hdr[2]), int(hdr[3])) == (H, W, H * W * 4)          # height, width, step = len(data)
-        q = raw[i * rec + 16:(i + 1) * rec].view(np.int32).reshape(1, 1, H, W)
+        hdr = raw[pos:pos + 16].view(np.uint32)
+        idx, step = int(hdr[0]), int(hdr[3]); seen.add(idx)
+        assert (int(hdr[1]), int(hdr[2])) == (H, W) and step > H * W * 4             # height, width, step = len(data)
+        data = raw[pos + 16:pos + 16 + step]
+        pos += 16 + step
+        q = data[:H * W * 4].view(np.int32).reshape(1, 1, H, W)
         s8 = pp.cvt_nv12_to_tensor_fast(*pp.split_side_by_side_nv12(frames[idx], H, 2 * W), W, H)
         assert (q == m.infer(s8)).all()
-    assert seen == set(range(N))
+        # the JPEG half: the left view, readable by the render tool's cv2.imdecode (publisher_member_function.py:93-95)
+        import cv2
+        im = cv2.imdecode(data[H * W * 4:], cv2.IMREAD_ANYCOLOR)
+        left = pp.split_side_by_side_nv12(frames[idx], H, 2 * W)[0]
+        ref = cv2.cvtColor(left.reshape(H * 3 // 2, W), cv2.COLOR_YUV2BGR_NV12)
+        assert im is not None and im.shape == ref.shape
+        assert 10 * np.log10(255.0 ** 2 / np.mean((im.astype(np.float64) - ref) ** 2)) > 30.0
+    assert pos == raw.size and seen == set(range(N))
     m.close()
+    # the reference's host pre-process path (preprocess=cpu) and a JPEG-less payload give the same s32 bytes
+    r = subprocess.run([EXE, "--model_file", str(tmp_path / "model.bin"), "--frames", str(tmp_path / "frames.nv12"),
+                        "--out", str(tmp_path / "out_cpu.bin"), "--model_in_h", str(H), "--model_in_w", str(W),
+                        "--K", str(K), "--D", str(D), "--precision", "tc", "--preprocess", "cpu", "--jpeg", "off"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw2 = np.frombuffer((tmp_path / "out_cpu.bin").read_bytes(), np.uint8)
+    rec = 16 + H * W * 4
+    assert raw2.size == N * rec
+    first = {int(raw[0:16].view(np.uint32)[0]): raw[16:16 + H * W * 4]}
+    for i in range(N):
+        hdr = raw2[i * rec:i * rec + 16].view(np.uint32)
+        assert int(hdr[3]) == H * W * 4
+        if int(hdr[0]) in first:
+            assert (raw2[i * rec + 16:(i + 1) * rec] == first[int(hdr[0])]).all()
+
+
+@pytest.mark.gpu
+def test_cli_multi_device(built_lib, tmp_path):
+    """--devices 0,1,...: one replica per GPU behind the same node (snb_pool_*); every frame is published exactly once."""
+    import torch
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    H, W, K, D, N = 64, 96, 3, 8, 24
+    (tmp_path / "model.bin").write_bytes(weights.make_blob(K, seed=1234))
+    frames = np.stack([synth.frame(H, W, 64, seed=300 + i) for i in range(N)])
+    (tmp_path / "frames.nv12").write_bytes(frames.tobytes())
+    r = subprocess.run([EXE, "--model_file", str(tmp_path / "model.bin"), "--frames", str(tmp_path / "frames.nv12"),
+                        "--out", str(tmp_path / "out.bin"), "--model_in_h", str(H), "--model_in_w", str(W), "--K", str(K), "--D", str(D),
+                        "--devices", ",".join(str(i) for i in range(ndev)), "--jpeg", "off"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert f"fed {N} frame(s), published {N}, dropped 0" in r.stderr
 
 
 @pytest.mark.gpu
