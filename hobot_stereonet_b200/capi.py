@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsnb200.so")
 SNB_OK, SNB_ERR_INVALID, SNB_ERR_MODEL, SNB_ERR_CUDA, SNB_ERR_NOMEM, SNB_ERR_BUSY = 0, -1, -2, -3, -4, -5
 PREC_FP32, PREC_TC_F16X2 = 0, 1
 FLAG_DEFER_WEIGHTS = 1024
-FLAG_KEEP_STAGES, FLAG_NO_GRAPH, FLAG_CORRECT_CHROMA, FLAG_NO_TENSOR, FLAG_NO_FUSE, FLAG_NO_STREAM, FLAG_PIPE, FLAG_NO_HBMCONV, FLAG_NO_COALESCE, FLAG_PAIR = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
+FLAG_KEEP_STAGES, FLAG_NO_GRAPH, FLAG_CORRECT_CHROMA, FLAG_NO_TENSOR, FLAG_NO_FUSE, FLAG_NO_STREAM, FLAG_NO_HBMCONV, FLAG_NO_COALESCE = 1, 2, 4, 8, 16, 32, 128, 256
 LAYOUT_NCHW, TENSOR_S8, TENSOR_S32 = 2, 1, 3
 
 
@@ -143,6 +143,7 @@ class Model:
         self._l = lib()
         self._h = C.c_void_p()
         self._cbs = {}
+        self._pending = []
         cfg = SnbConfig(C.sizeof(SnbConfig), height, width, K, D, max_batch, device, task_num, precision, flags,
                         model_file.encode() if model_file else None, None, 0)
         self._wbuf = None
@@ -211,19 +212,26 @@ class Model:
         return out
 
     def infer_async(self, s8, out, done=None, timeout_ms: int = -1, nv12: bool = False):
+        fn = self._l.snb_infer_nv12_async if nv12 else self._l.snb_infer_async
+        if done is None:
+            # no Python callback: the library's worker thread never has to take the GIL for this call.  The buffers
+            # stay referenced until wait_all() (the caller must not free them earlier anyway).
+            self._pending.append((s8, out))
+            if len(self._pending) > 4096:
+                del self._pending[:2048]             # far more than task_num calls ago: long finished
+            self._check(fn(self._h, _ptr(s8), _ptr(out), s8.shape[0], C.cast(None, DONE_FN), None, timeout_ms))
+            return
         key = id(out)
 
         def _cb(user, status, stat):
             st = stat.contents
             try:
-                if done:
-                    done(status, {"gpu_ms": st.gpu_ms, "infer_time_ms": st.infer_time_ms})
+                done(status, {"gpu_ms": st.gpu_ms, "infer_time_ms": st.infer_time_ms})
             finally:
                 self._cbs.pop(key, None)
 
         cb = DONE_FN(_cb)
         self._cbs[key] = (cb, s8, out)      # keep buffers and the thunk alive until the callback fired
-        fn = self._l.snb_infer_nv12_async if nv12 else self._l.snb_infer_async
         r = fn(self._h, _ptr(s8), _ptr(out), s8.shape[0], cb, None, timeout_ms)
         if r < 0:
             self._cbs.pop(key, None)
@@ -235,6 +243,7 @@ class Model:
 
     def wait_all(self):
         self._check(self._l.snb_wait_all(self._h))
+        self._pending.clear()
 
     def pass_count(self) -> int:
         return int(self._l.snb_get_pass_count(self._h))

@@ -217,12 +217,17 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
       if (un.cc != cur_cc) {
         // all four epilogue warps use the same 32 biases; a named barrier keeps the refill ordered within the group
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x - 64 < 32) s_bias[threadIdx.x - 64] = (int)(threadIdx.x - 64) < p.nbias ? p.bias[un.cc * NCO + (threadIdx.x - 64)] : 0.f;
+        // partial rows live in the accumulator domain (weights x 2^k): so does the bias; finished values are multiplied by 2^-k
+        if (threadIdx.x - 64 < 32) s_bias[threadIdx.x - 64] = (int)(threadIdx.x - 64) < p.nbias ? p.bias[un.cc * NCO + (threadIdx.x - 64)] / p.wsc : 0.f;
         asm volatile("bar.sync 1, 128;" ::: "memory");
         cur_cc = un.cc;
       }
       const int opx = un.x0 + m;
       const bool col_ok = opx < p.W;
+      // MMAs that accumulate into one TMEM accumulator of a job: (valid depth taps) x (16-channel chunks) x 3 kernel columns,
+      // x 3 when hi*hi, hi*lo and lo*hi share the accumulator; feeds the round-toward-zero compensation (common.cuh)
+      const int ndz = min(un.d + p.kz - 1 - zpad, p.D - 1) - max(un.d - zpad, 0) + 1;
+      const float kn = p.rzk * (float)(ndz * p.nk16 * ((SPLIT || NCO == 16) ? 3 : 9));
       if constexpr (NCO == 32) {
         const __half* res = static_cast<const __half*>(p.res.p);
         __half* out = static_cast<__half*>(p.out.p);
@@ -277,7 +282,7 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
               if (cb >= p.ncb_out) continue;                 // Cout < 32: the slice's upper channel blocks do not exist
               float g[8];
 #pragma unroll
-              for (int q = 0; q < 8; ++q) g[q] = f[cb * 8 + q];
+              for (int q = 0; q < 8; ++q) g[q] = rz_comp(f[cb * 8 + q], kn) * p.wsc;   // truncation loss back, out of the 2^k weight scale
               if (res) {
                 const __half2* h2 = reinterpret_cast<const __half2*>(&rh[cb]);
                 const __half2* l2 = reinterpret_cast<const __half2*>(&rl[cb]);
@@ -341,7 +346,7 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
           if (++ts == (uint32_t)p.nslots) { ts = 0; fpar ^= 1; }
           if (ok) {
             const float r = rr.f + (__half2float(__ushort_as_half(rr.h)) + __half2float(__ushort_as_half(rr.l)));
-            float f = a0 + (v2[0] + (v2[1] + v2[2])) + r;   // hi*hi + (hi*lo + lo*hi)
+            float f = fmaf(rz_comp(a0 + (v2[0] + (v2[1] + v2[2])), kn), p.wsc, r);   // hi*hi + (hi*lo + lo*hi), truncation loss back, out of the 2^k weight scale
             if (p.relu) f = fmaxf(f, 0.f);
             p.out_plane[o] = f;
           }
@@ -361,7 +366,7 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
 // ---- host side -----------------------------------------------------------------------------------
 // Weight packing: [cc][k16][dz][kx][K half][2*3*NCO rows][8]: rows [W_hi: ky*NCO + co | W_lo: 3*NCO + ky*NCO + co]
 // ks = 1: the single tap lands at the centre (ky = kx = 1) of an otherwise zero 3x3; cin is padded up to a multiple of 16.
-void cs_pack_weights(const float* W, int cout, int cin, int kz, int ks, int NCO, std::vector<__half>& out) {
+void cs_pack_weights(const float* W, int cout, int cin, int kz, int ks, int NCO, int wlog2, std::vector<__half>& out) {
   const int ccs = NCO == 32 ? (cout + 31) / 32 : 1, nk16 = (cin + 15) / 16, ncol = 3 * NCO;
   out.assign((size_t)ccs * nk16 * kz * 3 * 2 * 2 * ncol * 8, __float2half(0.f));
   for (int co = 0; co < cout; ++co)
@@ -370,7 +375,7 @@ void cs_pack_weights(const float* W, int cout, int cin, int kz, int ks, int NCO,
         for (int ky = 0; ky < 3; ++ky)
           for (int kx = 0; kx < 3; ++kx) {
             if (ks == 1 && (ky != 1 || kx != 1)) continue;
-            const float v = ks == 1 ? W[((size_t)co * cin + ci) * kz + dz] : W[((((size_t)co * cin + ci) * kz + dz) * 3 + ky) * 3 + kx];
+            const float v = ldexpf(ks == 1 ? W[((size_t)co * cin + ci) * kz + dz] : W[((((size_t)co * cin + ci) * kz + dz) * 3 + ky) * 3 + kx], wlog2);
             const __half hi = __float2half_rn(v);
             const __half lo = __float2half_rn(v - __half2float(hi));
             const int cc = NCO == 32 ? co / 32 : 0, cl = NCO == 32 ? co % 32 : co;
@@ -456,11 +461,13 @@ static cudaError_t cs_launch_t(CsParams p, int grid, size_t smem, cudaStream_t s
   return e;
 }
 
-cudaError_t launch_conv_stream(const CsPlan& plan, int N, const void* w, const float* bias, const Tens* out, const Tens* res,
+cudaError_t launch_conv_stream(const CsPlan& plan, int N, const void* w, int wlog2, const float* bias, const Tens* out, const Tens* res,
                                float* out_plane, const float* res_plane, int res_c8_ch0, int relu, int ostride, cudaStream_t st) {
   CsParams p = plan.p;
   p.ostride = ostride;
   p.N = N; p.w = static_cast<const __half*>(w); p.bias = bias; p.relu = relu;
+  p.rzk = rz_unit();
+  p.wsc = ldexpf(1.f, -wlog2);
   if (out) p.out = view(*out);
   p.res_mode = 0;
   if (res) { p.res = view(*res); p.res_mode = res_c8_ch0 ? 1 : 0; }

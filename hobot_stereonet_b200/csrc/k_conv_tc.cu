@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcConvParams p)
 #pragma unroll
         for (int c = 0; c < 16; ++c) acc[r][c] = 0.f;
 
+      const float kn = p.rzk * (p.cin8 ? 2.f : 3.f);      // MMAs per main chain: the kernel columns of one chunk (common.cuh rz_comp)
       for (int k16 = 0; k16 < p.nk16; ++k16) {
         for (int dz = 0; dz < p.kz; ++dz) {
           const int zin = tc.d + dz - zpad;
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcConvParams p)
             const size_t o = (size_t)tc.n * p.out.ss + ((size_t)cbo * p.D + tc.d) * p.out.slice + ((size_t)y * p.out.ws + x) * 8;
             float f[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = acc[r][jb * 8 + j] + __ldg(p.bias + co0 + jb * 8 + j);
+            for (int j = 0; j < 8; ++j) f[j] = fmaf(rz_comp(acc[r][jb * 8 + j], kn), p.wsc, __ldg(p.bias + co0 + jb * 8 + j));   // truncation loss back, out of the 2^k weight scale
             if (res) {
               const size_t ro = (size_t)tc.n * p.res.ss + ((size_t)cbo * p.D + tc.d) * p.res.slice + ((size_t)y * p.res.ws + x) * 8;
               const uint4 rh = __ldg(reinterpret_cast<const uint4*>(res + ro));
@@ -345,13 +346,15 @@ static void launch_r(const TcConvParams& p, int grid, size_t smem, cudaStream_t 
   launch_k(k_conv_tc<R>, grid, TC_THREADS, smem, st, p);
 }
 
-cudaError_t launch_conv_tc(const TcConvPlan& plan, int N, const void* w, const float* bias, const Tens* res, int relu,
+cudaError_t launch_conv_tc(const TcConvPlan& plan, int N, const void* w, int wlog2, const float* bias, const Tens* res, int relu,
                            int num_sms, cudaStream_t st) {
   TcConvParams p = plan.p;
   p.N = N; p.w = static_cast<const __half*>(w); p.bias = bias; p.relu = relu;
   if (res) p.res = view(*res);
   p.total_tiles = N * p.D * p.tiles_y * p.tiles_x * p.ccs;
   { static const int dbg = getenv("SNB_TC_DEBUG") ? atoi(getenv("SNB_TC_DEBUG")) : 0; p.dbg = dbg; }
+  p.rzk = rz_unit();
+  p.wsc = ldexpf(1.f, -wlog2);
   static const int prof = getenv("SNB_TC_PROF") ? atoi(getenv("SNB_TC_PROF")) : 0;
   static long long* d_prof = nullptr;
   if (prof && !d_prof) cudaMalloc(&d_prof, 256 * 16 * sizeof(long long));
@@ -378,7 +381,7 @@ cudaError_t launch_conv_tc(const TcConvPlan& plan, int N, const void* w, const f
 // Weight packing for k_conv_tc: [cc][k16][dz][kx][chunk 2][192 rows][8] fp16 from canonical
 // [Cout][Cin][kz][3][3] fp32; row = part*96 + half*48 + ky*16 + (co % 16), part 0 = W_hi, 1 = W_lo,
 // half = which 16 of the tile's 32 channels (one epilogue warp set each).
-void tc_pack_weights(const float* W, int cout, int cin, int kz, int NT, std::vector<__half>& out) {
+void tc_pack_weights(const float* W, int cout, int cin, int kz, int NT, int wlog2, std::vector<__half>& out) {
   if (NT == 8) {
     // cin8 packing: [cc][tap pair g][K half = kx - 2g][192 rows][8 ch]; the half of pair 1 that would be kx = 3 stays zero
     const int ccs = cout / TC_NT;
@@ -387,7 +390,7 @@ void tc_pack_weights(const float* W, int cout, int cin, int kz, int NT, std::vec
       for (int ci = 0; ci < cin; ++ci)
         for (int ky = 0; ky < 3; ++ky)
           for (int kx = 0; kx < 3; ++kx) {
-            const float v = W[(((size_t)co * cin + ci) * 3 + ky) * 3 + kx];
+            const float v = ldexpf(W[(((size_t)co * cin + ci) * 3 + ky) * 3 + kx], wlog2);
             const __half hi = __float2half_rn(v);
             const __half lo = __float2half_rn(v - __half2float(hi));
             const int cc = co / TC_NT, cl = co % TC_NT;
@@ -405,7 +408,7 @@ void tc_pack_weights(const float* W, int cout, int cin, int kz, int NT, std::vec
       for (int dz = 0; dz < kz; ++dz)
         for (int ky = 0; ky < 3; ++ky)
           for (int kx = 0; kx < 3; ++kx) {
-            const float v = W[((((size_t)co * cin + ci) * kz + dz) * 3 + ky) * 3 + kx];
+            const float v = ldexpf(W[((((size_t)co * cin + ci) * kz + dz) * 3 + ky) * 3 + kx], wlog2);
             const __half hi = __float2half_rn(v);
             const __half lo = __float2half_rn(v - __half2float(hi));
             const int cc = co / TC_NT, cl = co % TC_NT, k16 = ci / 16, chunk = (ci % 16) / 8, e = ci % 8;

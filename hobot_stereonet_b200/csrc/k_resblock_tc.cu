@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
     bulk_load(s_wb, p.wb, RB_W_BYTES, w_full);
   }
   if (warp == 1) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
-  if (threadIdx.x >= 64 && threadIdx.x < 128) s_bias[threadIdx.x - 64] = threadIdx.x < 96 ? p.ba[threadIdx.x - 64] : p.bb[threadIdx.x - 96];
+  // biases in the accumulator domain of their convolution (weights x 2^k, common.cuh weight_scale_log2)
+  if (threadIdx.x >= 64 && threadIdx.x < 128) s_bias[threadIdx.x - 64] = threadIdx.x < 96 ? p.ba[threadIdx.x - 64] / p.wsa : p.bb[threadIdx.x - 96] / p.wsb;
   // the y ring's columns >= 128 are read by shifted taps of masked pixels only; keep them finite
   for (int i = threadIdx.x; i < (int)(RB_YSLOTS * p.slot_bytes / 16); i += RB_THREADS)
     reinterpret_cast<uint4*>(s_y)[i] = make_uint4(0, 0, 0, 0);
@@ -265,6 +266,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
     const int m = (warp & 3) * 32 + lane;     // TMEM lane = M row = pixel within the 128-wide window
     const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t sy_addr = smem_u32(s_y) + (uint32_t)m * 16;
+    const float kna = p.rzk * 6.f;            // MMAs per conv_a main accumulator: 2 chunks x 3 kernel columns
     uint32_t na = 0, ny = 0;
     long long t_emit = 0;
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
           for (int cb = 0; cb < 4; ++cb) {
             float g[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) g[q] = ok ? fmaxf(f[cb * 8 + q], 0.f) : 0.f;
+            for (int q = 0; q < 8; ++q) g[q] = ok ? fmaxf(rz_comp(f[cb * 8 + q], kna), 0.f) * p.wsa : 0.f;   // truncation loss back (common.cuh), ReLU, out of the weight scale
             uint4 oh, ol;
             rb_split8(g, oh, ol);
             const uint32_t a = sy_addr + ys * p.slot_bytes + (uint32_t)cb * p.sub_bytes;
@@ -334,6 +336,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
     const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + RB_BBASE;
     const __half* res = static_cast<const __half*>(p.res.p);
     __half* out = static_cast<__half*>(p.out.p);
+    const float knb = p.rzk * ((p.dbg & 16) ? 12.f : 18.f);      // conv_b merged accumulator: 2 chunks x 3 columns x {hi*hi, hi*lo, lo*hi}
     uint32_t nb = 0;
     long long t_emit = 0;
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
@@ -380,8 +383,8 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
               for (int j = 0; j < 4; ++j) {
                 const float2 a = __half22float2(h2[j]), b = __half22float2(l2[j]);
                 const int c = jb * 8 + 2 * j;
-                f[2 * j] = fmaxf(b0[hf * 16 + c] + v[c] + (a.x + b.x), 0.f);
-                f[2 * j + 1] = fmaxf(b0[hf * 16 + c + 1] + v[c + 1] + (a.y + b.y), 0.f);
+                f[2 * j] = fmaxf(fmaf(rz_comp(b0[hf * 16 + c] + v[c], knb), p.wsb, a.x + b.x), 0.f);
+                f[2 * j + 1] = fmaxf(fmaf(rz_comp(b0[hf * 16 + c + 1] + v[c + 1], knb), p.wsb, a.y + b.y), 0.f);
               }
               uint4 oh, ol;
               rb_split8(f, oh, ol);
@@ -440,10 +443,12 @@ cudaError_t resblock_tc_plan(RbPlan* plan, const Tens& in, const Tens& out, cons
   return cudaSuccess;
 }
 
-cudaError_t launch_resblock_tc(const RbPlan& plan, int N, const void* wa, const void* wb, const float* ba, const float* bb,
-                               cudaStream_t st) {
+cudaError_t launch_resblock_tc(const RbPlan& plan, int N, const void* wa, const void* wb, int wlog2a, int wlog2b, const float* ba,
+                               const float* bb, cudaStream_t st) {
   RbParams p = plan.p;
   p.N = N; p.wa = static_cast<const __half*>(wa); p.wb = static_cast<const __half*>(wb); p.ba = ba; p.bb = bb;
+  p.rzk = rz_unit();
+  p.wsa = ldexpf(1.f, -wlog2a); p.wsb = ldexpf(1.f, -wlog2b);
   { static const int dbg = getenv("SNB_RB_DEBUG") ? atoi(getenv("SNB_RB_DEBUG")) : 0; p.dbg = (long)p.H * p.W >= 400000 ? dbg : 0; }
   // row chunks: about one unit per SM (every unit pays 4 halo rows, but an idle SM pays more), at least 2 rows each
   const int rc_max = cdiv(p.H, p.dil);

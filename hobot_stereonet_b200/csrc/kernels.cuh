@@ -10,29 +10,21 @@ cudaError_t launch_conv_to1(const ConvTo1Params& p, cudaStream_t st);
 
 // k_conv_tc.cu — tcgen05 implicit-GEMM convolution on split-fp16 tensors (M1, M3, M5)
 cudaError_t tc_conv_plan(TcConvPlan* plan, const Tens& in, const Tens& out, int cin, int cout, int dil, int kz, int num_sms);
-cudaError_t launch_conv_tc(const TcConvPlan& plan, int N, const void* w, const float* bias, const Tens* res, int relu,
+cudaError_t launch_conv_tc(const TcConvPlan& plan, int N, const void* w, int wlog2, const float* bias, const Tens* res, int relu,
                            int num_sms, cudaStream_t st);
-void tc_pack_weights(const float* W, int cout, int cin, int kz, int NT, std::vector<__half>& out);
+// packs w * 2^wlog2 (common.cuh weight_scale_log2); the launchers take the same wlog2 and undo it in the epilogue
+void tc_pack_weights(const float* W, int cout, int cin, int kz, int NT, int wlog2, std::vector<__half>& out);
 
 // k_resblock_tc.cu — fused residual block (conv_a + ReLU + conv_b + residual + ReLU), 32 channels (M1 layer1, M5)
 cudaError_t resblock_tc_plan(RbPlan* plan, const Tens& in, const Tens& out, const Tens& res, int dil, int num_sms);
-cudaError_t launch_resblock_tc(const RbPlan& plan, int N, const void* wa, const void* wb, const float* ba, const float* bb,
-                               cudaStream_t st);
+cudaError_t launch_resblock_tc(const RbPlan& plan, int N, const void* wa, const void* wb, int wlog2a, int wlog2b, const float* ba,
+                               const float* bb, cudaStream_t st);
 
 // k_conv_stream.cu — streaming tcgen05 convolution, weights resident in shared memory (M1, M3, M5)
 cudaError_t conv_stream_plan(CsPlan* plan, const Tens& in, int cin, int cout, int dil, int kz, int num_sms);
-cudaError_t launch_conv_stream(const CsPlan& plan, int N, const void* w, const float* bias, const Tens* out, const Tens* res,
+cudaError_t launch_conv_stream(const CsPlan& plan, int N, const void* w, int wlog2, const float* bias, const Tens* out, const Tens* res,
                                float* out_plane, const float* res_plane, int res_c8_ch0, int relu, int ostride, cudaStream_t st);
-void cs_pack_weights(const float* W, int cout, int cin, int kz, int ks, int NCO, std::vector<__half>& out);
-
-// k_conv_pipe.cu — a chain of same-shape streaming convolutions as a layer pipeline in one launch (M1: layer2)
-cudaError_t conv_pipe_plan(CsPlan* plan, const Tens& in, int ch, int num_sms);
-int conv_pipe_layers_per_launch(const CsPlan& plan, int N, int nlayers);
-cudaError_t launch_conv_pipe(const CsPlan& plan, int N, const CsLayer* d_layers, int nlayers, int* d_done, cudaStream_t st);
-
-// k_conv_pair.cu — one 64-channel BasicBlock (conv_a + conv_b) as one launch of thread-block clusters, y rows through DSMEM (M1: layer2)
-cudaError_t conv_pair_plan(CsPlan* plan, const Tens& in, int ch, int num_sms);
-cudaError_t launch_conv_pair(const CsPlan& plan, int N, const CsLayer& la, const CsLayer& lb, cudaStream_t st);
+void cs_pack_weights(const float* W, int cout, int cin, int kz, int ks, int NCO, int wlog2, std::vector<__half>& out);
 
 // k_conv_hbm.cu — few-input-channel convolutions of the tensor path (firstconv.0, refinement conv_in): CUDA cores, weights in the constant bank
 void conv_first_pack(const float* W, const float* bias, int cin, ConvFirstParams* p);

@@ -98,6 +98,7 @@ static int pack_conv(snb_ctx* c, const std::string& name) {
   const bool is3d = W.shape.size() == 5;
   cw.kz = is3d ? W.shape[2] : 1;
   cw.ks = W.shape.back();
+  cw.wlog2 = weight_scale_log2(W.data.data(), W.data.size());
   const int ntap = cw.ks * cw.ks, cbin = (cw.cin + 7) / 8;
   std::vector<float> packed;
   if (cw.cout == 1) {
@@ -205,7 +206,7 @@ struct Builder {
     const int NT = cw.cin <= 8 ? 8 : 32;   // packing id: 32 = 16-channel K chunks, 8 = "cin8" tap-pair packing
     if (!cw.w_tc.count(NT)) {
       std::vector<__half> packed;
-      tc_pack_weights(c->wts[name + ".weight"].data.data(), cw.cout, cw.cin, cw.kz, NT, packed);
+      tc_pack_weights(c->wts[name + ".weight"].data.data(), cw.cout, cw.cin, cw.kz, NT, cw.wlog2, packed);
       __half* dw = nullptr;
       if (cudaMalloc(&dw, packed.size() * sizeof(__half)) != cudaSuccess) { fail = true; return nullptr; }
       cudaMemcpy(dw, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice);
@@ -220,7 +221,7 @@ struct Builder {
     const int key = 100 + nco;
     if (!cw.w_tc.count(key)) {
       std::vector<__half> packed;
-      cs_pack_weights(c->wts[name + ".weight"].data.data(), cw.cout, cw.cin, cw.kz, cw.ks, nco, packed);
+      cs_pack_weights(c->wts[name + ".weight"].data.data(), cw.cout, cw.cin, cw.kz, cw.ks, nco, cw.wlog2, packed);
       __half* dw = nullptr;
       if (cudaMalloc(&dw, packed.size() * sizeof(__half)) != cudaSuccess) { fail = true; return nullptr; }
       cudaMemcpy(dw, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice);
@@ -262,104 +263,11 @@ struct Builder {
     const double px = (double)nmul * in.h * in.w;
     op.flops = 2.0 * 2.0 * px * 32 * 32 * 9;
     op.bytes = 4.0 * px * 32 * (&res == &in || res.p == in.p ? 2 : 3);
-    op.fn = [plan, nmul, wa, wb, ba, bb](int B, cudaStream_t st) { return launch_resblock_tc(plan, nmul * B, wa, wb, ba, bb, st); };
+    const int la = ia->second.wlog2, lb = ib->second.wlog2;
+    op.fn = [plan, nmul, wa, wb, la, lb, ba, bb](int B, cudaStream_t st) { return launch_resblock_tc(plan, nmul * B, wa, wb, la, lb, ba, bb, st); };
     c->n_tc_convs += 2;
     c->ops.push_back(op);
     return out;
-  }
-
-  // one identity BasicBlock (conv_a -> ReLU -> conv_b -> + x -> ReLU) of 64 channels as ONE cluster launch (k_conv_pair.cu)
-  bool pair(const std::string& prefix, const Tens& x, int nmul, int dil, Tens* result) {
-    static const int env_pair = getenv("SNB_PAIR") ? atoi(getenv("SNB_PAIR")) : -1;
-    // opt-in: 15 us in-kernel per block against 2 x 7 us, but a cluster launch costs ~5 us more than a plain one inside the
-    // CUDA graph: 1.646 ms per pass with it, 1.573 without (k_conv_pair.cu header)
-    const bool want = env_pair >= 0 ? env_pair != 0 : (c->cfg.flags & SNB_FLAG_PAIR) != 0;
-    if (c->planes != 2 || !want || (c->cfg.flags & (SNB_FLAG_NO_TENSOR | SNB_FLAG_NO_STREAM | SNB_FLAG_KEEP_STAGES)) || dil != 1) return false;
-    auto ia = c->convs.find(prefix + ".conv_a"), ib = c->convs.find(prefix + ".conv_b");
-    if (ia == c->convs.end() || ib == c->convs.end() || ia->second.cin != x.c || ia->second.cout != x.c || ib->second.cin != x.c ||
-        ib->second.cout != x.c || ia->second.ks != 3 || ib->second.ks != 3 || ia->second.kz != 1) return false;
-    CsPlan plan;
-    if (conv_pair_plan(&plan, x, x.c, c->num_sms) != cudaSuccess) return false;
-    Tens o = alloc(nmul, x.c, 1, x.h, x.w, x.pad);
-    CsLayer la{}, lb{};
-    la.in = view(x); la.w = stream_weights(prefix + ".conv_a", ia->second, 32); la.bias = ia->second.b; la.relu = 1;
-    lb.out = view(o); lb.res = view(x); lb.has_res = 1; lb.w = stream_weights(prefix + ".conv_b", ib->second, 32);
-    lb.bias = ib->second.b; lb.relu = 1;
-    if (!la.w || !lb.w) return false;
-    Op op; op.name = prefix + " [tc-pair]";
-    const double px = (double)nmul * x.h * x.w;
-    op.flops = 2 * 2.0 * px * x.c * x.c * 9;
-    op.bytes = 4.0 * px * x.c * 3;
-    op.fn = [plan, la, lb, nmul](int B, cudaStream_t st) { return launch_conv_pair(plan, nmul * B, la, lb, st); };
-    c->n_tc_convs += 2;
-    c->ops.push_back(op);
-    *result = o;
-    return true;
-  }
-
-  // blocks [first, first + nblk) of `layer` (identity BasicBlocks on tensors of x's geometry) as a layer pipeline
-  // (k_conv_pipe.cu): one CTA per (convolution, view, strip, channel slice), rows handed from layer to layer through L2
-  bool chain(const std::string& layer, int first, int nblk, const Tens& x, int nmul, int dil, Tens* result) {
-    // opt-in: measured 434 us for layer2's 30 convolutions against ~295 us as separate launches (k_conv_pipe.cu header)
-    static const int env_pipe = getenv("SNB_PIPE") ? atoi(getenv("SNB_PIPE")) : -1;
-    const bool want = env_pipe >= 0 ? env_pipe != 0 : (c->cfg.flags & SNB_FLAG_PIPE) != 0;
-    if (c->planes != 2 || !want || (c->cfg.flags & (SNB_FLAG_NO_TENSOR | SNB_FLAG_NO_STREAM | SNB_FLAG_KEEP_STAGES)) || nblk < 1 || dil != 1) return false;
-    CsPlan plan, splan;
-    if (conv_pipe_plan(&plan, x, x.c, c->num_sms) != cudaSuccess) return false;
-    if (conv_stream_plan(&splan, x, x.c, x.c, dil, 1, c->num_sms) != cudaSuccess) return false;
-    std::vector<CsLayer> layers;
-    std::vector<Tens> outs;       // per layer: its own output tensor (rows of several layers are in flight at once)
-    Tens cur = x;
-    double flops = 0, bytes = 0;
-    for (int bi = first; bi < first + nblk; ++bi) {
-      const std::string pb = layer + "." + std::to_string(bi);
-      auto ia = c->convs.find(pb + ".conv_a"), ib = c->convs.find(pb + ".conv_b");
-      if (ia == c->convs.end() || ib == c->convs.end() || ia->second.cin != x.c || ia->second.cout != x.c || ib->second.cin != x.c ||
-          ib->second.cout != x.c || ia->second.ks != 3 || ib->second.ks != 3 || ia->second.kz != 1) {
-        for (const Tens& t : outs) free(t);
-        return false;
-      }
-      Tens a = alloc(nmul, x.c, 1, x.h, x.w, x.pad), o = alloc(nmul, x.c, 1, x.h, x.w, x.pad);
-      CsLayer la{}, lb{};
-      la.in = view(cur); la.out = view(a); la.w = stream_weights(pb + ".conv_a", ia->second, 32); la.bias = ia->second.b; la.relu = 1;
-      lb.in = view(a); lb.out = view(o); lb.res = view(cur); lb.has_res = 1; lb.w = stream_weights(pb + ".conv_b", ib->second, 32);
-      lb.bias = ib->second.b; lb.relu = 1;
-      if (!la.w || !lb.w) return false;
-      layers.push_back(la); layers.push_back(lb);
-      outs.push_back(a); outs.push_back(o);
-      const double px = (double)nmul * x.h * x.w;
-      flops += 2 * 2.0 * px * x.c * x.c * 9;
-      bytes += 4.0 * px * x.c * 5;
-      cur = o;
-    }
-    for (size_t i = 0; i + 1 < outs.size(); ++i) free(outs[i]);     // reusable by the ops AFTER this one
-    CsLayer* d_layers = nullptr; int* d_done = nullptr;
-    const size_t n_done = layers.size() * (size_t)c->num_sms;
-    if (cudaMalloc(&d_layers, layers.size() * sizeof(CsLayer)) != cudaSuccess || cudaMalloc(&d_done, n_done * sizeof(int)) != cudaSuccess) { fail = true; return false; }
-    cudaMemcpy(d_layers, layers.data(), layers.size() * sizeof(CsLayer), cudaMemcpyHostToDevice);
-    c->wallocs.push_back(d_layers); c->wallocs.push_back(d_done);
-    Op op; op.name = layer + "." + std::to_string(first) + "-" + std::to_string(first + nblk - 1) + " [tc-pipe x" + std::to_string(layers.size()) + "]";
-    op.flops = flops; op.bytes = bytes;
-    const int nl = (int)layers.size();
-    const Tens xin = x;
-    op.fn = [plan, splan, layers, outs, xin, d_layers, d_done, nl, nmul](int B, cudaStream_t st) {
-      if (conv_pipe_layers_per_launch(plan, nmul * B, nl) >= 2) return launch_conv_pipe(plan, nmul * B, d_layers, nl, d_done, st);
-      // too many units per layer for a pipeline (large batches): the same layers, one k_conv_stream launch each
-      for (int l = 0; l < nl; ++l) {
-        CsPlan sp = splan;
-        sp.p.in = layers[l].in;
-        Tens out_t = outs[l];
-        Tens res_t = l >= 2 ? outs[l - 2] : xin;           // conv_b's residual = the block's input
-        cudaError_t e = launch_conv_stream(sp, nmul * B, layers[l].w, layers[l].bias, &out_t, layers[l].has_res ? &res_t : nullptr,
-                                           nullptr, nullptr, 0, layers[l].relu, 1, st);
-        if (e != cudaSuccess) return e;
-      }
-      return cudaSuccess;
-    };
-    c->n_tc_convs += nl;
-    c->ops.push_back(op);
-    *result = cur;
-    return true;
   }
 
   Tens conv(const std::string& name, const Tens& in, int nmul, int stride, int dil, bool relu, const Tens* res,
@@ -394,8 +302,9 @@ struct Builder {
       const bool has_res = res != nullptr;
       const Tens rt = res ? *res : Tens();
       const int rl = relu ? 1 : 0;
-      op.fn = [splan, nmul, dw, bias, out, has_res, rt, rl, stride](int B, cudaStream_t st) {
-        return launch_conv_stream(splan, nmul * B, dw, bias, &out, has_res ? &rt : nullptr, nullptr, nullptr, 0, rl, stride, st);
+      const int wl = cw.wlog2;
+      op.fn = [splan, nmul, dw, wl, bias, out, has_res, rt, rl, stride](int B, cudaStream_t st) {
+        return launch_conv_stream(splan, nmul * B, dw, wl, bias, &out, has_res ? &rt : nullptr, nullptr, nullptr, 0, rl, stride, st);
       };
       op.name += " [tc-stream]";
       ++c->n_tc_convs;
@@ -412,8 +321,9 @@ struct Builder {
       const bool has_res = res != nullptr;
       const Tens rt = res ? *res : Tens();
       const int sms = c->num_sms, rl = relu ? 1 : 0;
-      op.fn = [plan, nmul, dw, bias, has_res, rt, rl, sms](int B, cudaStream_t st) {
-        return launch_conv_tc(plan, nmul * B, dw, bias, has_res ? &rt : nullptr, rl, sms, st);
+      const int wl = cw.wlog2;
+      op.fn = [plan, nmul, dw, wl, bias, has_res, rt, rl, sms](int B, cudaStream_t st) {
+        return launch_conv_tc(plan, nmul * B, dw, wl, bias, has_res ? &rt : nullptr, rl, sms, st);
       };
       op.name += " [tc]";
       ++c->n_tc_convs;
@@ -449,8 +359,9 @@ struct Builder {
       const int rl = relu ? 1 : 0;
       float* op_ = out.p;
       Op op; op.name = name + " [tc-stream]";
-      op.fn = [splan, dw, bias, op_, has_res, rt, rl](int B, cudaStream_t st) {
-        return launch_conv_stream(splan, B, dw, bias, nullptr, has_res ? &rt : nullptr, op_, nullptr, 1, rl, 1, st);
+      const int wl = cw.wlog2;
+      op.fn = [splan, dw, wl, bias, op_, has_res, rt, rl](int B, cudaStream_t st) {
+        return launch_conv_stream(splan, B, dw, wl, bias, nullptr, has_res ? &rt : nullptr, op_, nullptr, 1, rl, 1, st);
       };
       const double px = (double)in.d * in.h * in.w;
       op.flops = 2.0 * px * cw.cin * 9 * cw.kz;
@@ -505,25 +416,6 @@ int build_plan(snb_ctx* c) {
     for (int bi = 0; bi < LAYER_BLOCKS[li - 1]; ++bi) {
       const std::string p = "backbone.layer" + std::to_string(li) + "." + std::to_string(bi);
       const int s = bi == 0 ? strides[li - 1] : 1, dil = li == 4 ? 2 : 1;
-      // opt-in experiments for layer2's identity blocks: all of them as one layer-pipelined launch (SNB_FLAG_PIPE) ...
-      if (bi == 1 && li == 2) {
-        const int nblk = LAYER_BLOCKS[li - 1] - 1;
-        Tens o;
-        if (b.chain(p.substr(0, p.rfind('.')), 1, nblk, x, 2, dil, &o)) {
-          b.free(x);
-          x = o;
-          break;
-        }
-      }
-      // ... or each of them as one thread-block-cluster launch (SNB_FLAG_PAIR)
-      if (li == 2 && bi >= 1 && s == 1) {
-        Tens o;
-        if (b.pair(p, x, 2, dil, &o)) {
-          b.free(x);
-          x = o;
-          continue;
-        }
-      }
       Tens sc = x;
       const bool ds = bi == 0 && li <= 3;
       if (ds) sc = b.conv(p + ".downsample", x, 2, s, 1, false, nullptr);

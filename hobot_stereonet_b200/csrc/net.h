@@ -27,6 +27,7 @@ struct ConvW {             // device-resident, kernel-specific packing of one co
   float* b = nullptr;      // [cout]
   float b0 = 0.f;          // bias of Cout=1 convs
   int cout = 0, cin = 0, ks = 1, kz = 1;
+  int wlog2 = 0;           // the tcgen05 packings hold w * 2^wlog2 (common.cuh weight_scale_log2)
 };
 
 struct Op {

@@ -51,9 +51,7 @@ enum {
   SNB_FLAG_NO_STREAM = 32,    /* diagnostics: tiled k_conv_tc / CUDA-core kernels instead of the streaming convolution */
   SNB_FLAG_NO_HBMCONV = 128,  /* diagnostics: firstconv.0 on the tcgen05 streaming kernel instead of k_conv_first (k_conv_hbm.cu) */
   SNB_FLAG_NO_COALESCE = 256, /* snb_infer_async: one pass per call even when max_batch > 1 (default: queued calls are merged into passes of up to max_batch pairs) */
-  SNB_FLAG_PAIR = 512,        /* experiment: 64-channel BasicBlocks as one thread-block-cluster launch with the intermediate rows handed over through distributed shared memory (k_conv_pair.cu; correct, not faster at one pair per pass) */
-  SNB_FLAG_DEFER_WEIGHTS = 1024, /* snb_create without a model: the weights arrive through snb_set_weights (multi-GPU init, snb_pool_create); until then every infer call returns SNB_ERR_MODEL */
-  SNB_FLAG_PIPE = 64          /* experiment: layer2's identity blocks as one layer-pipelined launch (k_conv_pipe.cu; correct but slower) */
+  SNB_FLAG_DEFER_WEIGHTS = 1024  /* snb_create without a model: the weights arrive through snb_set_weights (multi-GPU init, snb_pool_create); until then every infer call returns SNB_ERR_MODEL */
 };
 
 /* Replaces dnn_node_para_ptr_->{model_file, model_task_type, task_num} (stereonet_node.cpp:136-144)

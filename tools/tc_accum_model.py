@@ -1,0 +1,196 @@
+#!/usr/bin/env python
+"""Bit-exact model of the tcgen05.mma kind::f16 accumulate (measured on a B200 by tools/ubench/mma_round_probe.py:
+0 mismatches over 3440 single-MMA cases, 768 of 768 chains of 6-24 MMAs reproduced exactly) and what it does to the
+convolution chains of this library.
+
+  hardware    acc' = RZ_fp32( sum_i RZ_u(x_i) ),  x_i = {acc, 16 exact fp16 x fp16 products},
+              u = 2^(emax - 25) with emax the largest exponent among the 17 addends (two guard bits below the fp32 ulp of
+              the largest addend), RZ = round toward zero.
+  consequence every MMA pulls its accumulator toward zero: E[err] = -(3/8 + ...) ulp(acc) * sign(acc) per MMA, a SYSTEMATIC
+              bias where IEEE fp32 (the reference float model) has zero-mean rounding.  Through ~70 layers of mostly
+              non-negative (post-ReLU) activations it adds up: profiles/r02_stage_*_d192.txt.
+
+This tool replays the model on REAL layer data (activations and weights of the CPU oracle at a small size, operands
+rounded to fp16 like the kernels' hi planes), chain by chain in the kernels' issue order, and fits the expected loss as
+      err = -kappa * sign(acc) * ulp(acc)
+per accumulator, for each chain length the kernels use.  kappa feeds the epilogue compensation (csrc/common.cuh
+RZ_KAPPA_PER_MMA): the drained accumulator gets +kappa * sign * ulp back, which removes the mean of the truncation loss
+and leaves its (zero-mean) scatter.
+usage: python tools/tc_accum_model.py [--samples 20000]
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import arch, prepost_ref as pp, synth, weights  # noqa: E402
+from oracle.stereonet_ref import Oracle  # noqa: E402
+
+
+def _exp(x):
+    """floor(log2 |x|) as float64, -inf... (a very small number) for zeros."""
+    m, e = np.frexp(x)
+    return np.where(x == 0, -1.0e4, e - 1.0)
+
+
+def rz(x, unit_log2):
+    u = np.exp2(unit_log2)
+    return np.trunc(x / u) * u
+
+
+def rz32(x):
+    return np.where(x == 0, 0.0, rz(x, _exp(x) - 23))
+
+
+def mma_chain(prods, acc0=None):
+    """prods [steps, 16, S] float64 exact products -> accumulator after every step [steps, S] (fp32-valued float64)."""
+    steps, k, S = prods.shape
+    acc = np.zeros(S) if acc0 is None else acc0.copy()
+    out = np.empty((steps, S))
+    for s in range(steps):
+        x = np.concatenate([acc[None], prods[s]], 0)
+        emax = _exp(x).max(0)
+        t = rz(x, emax - 25)
+        acc = rz32(t.sum(0))
+        out[s] = acc
+    return out
+
+
+def ulp(x):
+    return np.exp2(_exp(x) - 23)
+
+
+def rz_fix(v, kn):
+    """the epilogue compensation: v + copysign(kn * ulp(v), v)"""
+    return v + np.sign(v) * kn * ulp(v)
+
+
+def half_hi(t):
+    return t.half().double()
+
+
+def capture_inputs(cfg, s8, wts, names):
+    got = {}
+
+    def rf(t, tag):
+        nm, kind = tag.rsplit(":", 1) if ":" in tag else (tag, "")
+        if kind == "a" and nm in names:
+            got[nm] = t.detach().clone()
+        return t
+
+    Oracle(cfg, wts, round_fn=rf).forward_norm(s8)
+    return got
+
+
+def sample_chain_products(x, w, dil, samples, rng, mode):
+    """x [N,C,(D,)H,W] activation (float), w [Cout,C,(kz,)3,3].  Returns per kernel row ky the products of `samples` random
+    output elements in the kernels' issue order: list over ky of [steps, 16, S].
+    mode "split": the main accumulator (hi x hi products only); "merged": one accumulator takes hi*hi, hi*lo, lo*hi of every
+    (chunk, kx) in that order (k_conv_stream with Cin = 32, conv_b of k_resblock_tc); "chain3": hi x hi, a fresh chain per
+    16-channel chunk (k_conv_tc), returned as [chunks][3, 16, S]."""
+    is3d = w.dim() == 5
+    xh, wh = half_hi(x), half_hi(w)
+    xl, wl = half_hi(x.double() - xh).numpy(), half_hi(w.double() - wh).numpy()
+    N, C = xh.shape[:2]
+    H, W = xh.shape[-2:]
+    D = xh.shape[2] if is3d else 1
+    Cout = wh.shape[0]
+    S = samples
+    n = rng.integers(0, N, S); co = rng.integers(0, Cout, S)
+    y = rng.integers(dil, H - dil, S); xx = rng.integers(dil, W - dil, S)
+    z = rng.integers(1, D - 1, S) if is3d else None
+    xn = xh.numpy(); wn = wh.numpy()
+    per_ky = []
+    for ky in range(3):
+        steps = []
+        for dz in (range(3) if is3d else [None]):
+            for k16 in range(C // 16):
+                for kx in range(3):
+                    ci = np.arange(k16 * 16, k16 * 16 + 16)
+                    yy = y + (ky - 1) * dil; xs = xx + (kx - 1) * dil
+                    if is3d:
+                        ia = (n[None, :], ci[:, None], (z + dz - 1)[None, :], yy[None, :], xs[None, :])
+                        iw = (co[None, :], ci[:, None], dz, ky, kx)
+                    else:
+                        ia = (n[None, :], ci[:, None], yy[None, :], xs[None, :])
+                        iw = (co[None, :], ci[:, None], ky, kx)
+                    steps.append(xn[ia] * wn[iw])
+                    if mode == "merged":
+                        steps.append(xn[ia] * wl[iw])
+                        steps.append(xl[ia] * wn[iw])
+        per_ky.append(np.stack(steps))
+    return per_ky
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--samples", type=int, default=20000)
+    args = ap.parse_args()
+    torch.set_num_threads(os.cpu_count())
+    cfg = arch.Config(136, 240, 3, 24)
+    frame = synth.frame(cfg.H, cfg.W, cfg.max_disp, seed=1235)
+    s8 = pp.cvt_nv12_to_tensor_fast(*pp.split_side_by_side_nv12(frame, cfg.H, 2 * cfg.W), cfg.W, cfg.H)
+    wts = weights.generate(cfg.K, seed=1234)
+    layers = [  # name, dilation, accumulator structure of the kernel that runs it
+        ("backbone.firstconv.1", 1, "merged"), ("backbone.layer1.1.conv_a", 1, "split"), ("backbone.layer1.1.conv_b", 1, "merged"),
+        ("backbone.layer2.5.conv_a", 1, "split"), ("backbone.layer2.5.conv_b", 1, "split"), ("backbone.layer3.1.conv_a", 1, "split"),
+        ("backbone.layer4.1.conv_b", 2, "split"), ("backbone.lastconv.0", 1, "chain3"), ("head.filter.0", 1, "chain3"), ("head.filter.2", 1, "split"),
+        ("head.conv3d_alone", 1, "split"), ("head.refine.0.blocks.3.conv_a", 8, "split"), ("head.refine.2.blocks.1.conv_a", 2, "split"),
+        ("head.refine.2.blocks.1.conv_b", 2, "merged"), ("head.refine.2.conv_out", 1, "split")]
+    acts = capture_inputs(cfg, s8, wts, {n for n, _, _ in layers})
+    rng = np.random.default_rng(3)
+    once = []
+    print(f"{'layer':44s} {'MMAs/acc':>8s} {'kappa':>8s} {'kappa/MMA':>9s} {'bias ulp':>9s} {'rms ulp':>8s} {'rms after':>9s}  (ulp of the accumulator)")
+    rows = []
+    for name, dil, mode in layers:
+        x = acts[name]; w = torch.from_numpy(wts[name + ".weight"])
+        if x.shape[1] % 16:
+            continue
+        per_ky = sample_chain_products(x, w, dil, args.samples, rng, "split" if mode == "chain3" else mode)
+        if mode == "chain3":       # k_conv_tc: every (depth tap, chunk) is its own chain of the three kx MMAs
+            per_ky = [p[i:i + 3] for p in per_ky for i in range(0, p.shape[0], 3)][:12]
+        name = f"{name} [{mode}]"
+        ks, bias, rms, rms2, nst, absb = [], [], [], [], per_ky[0].shape[0], []
+        for prods in per_ky:
+            acc = mma_chain(prods)[-1]
+            exact = prods.sum((0, 1))
+            sel = np.abs(acc) > 0
+            u = ulp(acc[sel]); sg = np.sign(acc[sel]); err = (acc - exact)[sel]
+            # least squares: err = -kappa * sg * u
+            kappa = -np.sum(err * sg * u) / np.sum(u * u)
+            ks.append(kappa)
+            bias.append(np.mean(err * sg / u)); rms.append(np.sqrt(np.mean((err / u) ** 2)))
+            rms2.append(np.sqrt(np.mean(((err + kappa * sg * u) / u) ** 2)))
+            pos = sg > 0                                        # what survives a ReLU: absolute bias before / after, one kappa per MMA for all layers
+            k_all = 0.22 * prods.shape[0]
+            absb.append((np.mean(err[pos]), np.mean((err + kappa * sg * u)[pos]), np.mean((err + k_all * sg * u)[pos]), np.sqrt(np.mean(err[pos] ** 2))))
+        k = float(np.mean(ks))
+        rows.append((name, nst, k))
+        # compensating ONCE, on the finished output value (sum of all its accumulators), instead of on every drained accumulator
+        accs = [mma_chain(pr)[-1] for pr in per_ky]
+        tot_hw = np.sum(accs, 0); tot_exact = np.sum([pr.sum((0, 1)) for pr in per_ky], 0)
+        sel = np.abs(tot_hw) > 0
+        u = ulp(tot_hw[sel]); sg = np.sign(tot_hw[sel]); err = (tot_hw - tot_exact)[sel]
+        k_tot = -np.sum(err * sg * u) / np.sum(u * u)
+        n_tot = sum(pr.shape[0] for pr in per_ky)
+        per_acc = np.sum([rz_fix(a, 0.21 * pr.shape[0]) for a, pr in zip(accs, per_ky)], 0)
+        pos = tot_hw > 0
+        once.append((name, n_tot, k_tot, k_tot / n_tot, np.mean((tot_hw - tot_exact)[pos]), np.mean((per_acc - tot_exact)[pos]),
+                     np.mean((rz_fix(tot_hw, k_tot) - tot_exact)[pos]), np.mean((rz_fix(tot_hw, 0.155 * n_tot) - tot_exact)[pos])))
+        ab = np.mean(np.array(absb), 0)
+        print(f"{name:44s} {nst:8d} {k:8.3f} {k / nst:9.4f} {np.mean(bias):9.3f} {np.mean(rms):8.3f} {np.mean(rms2):9.3f}   "
+              f"abs bias(acc>0) {ab[0]:+.2e} -> fitted {ab[1]:+.2e} / 0.22n {ab[2]:+.2e}   rms {ab[3]:.2e}")
+    print("\ncompensation applied once to the finished value (sum of its accumulators; chain3 rows: the 12 sampled chains)")
+    print(f"{'layer':44s} {'MMAs':>5s} {'kappa':>7s} {'/MMA':>7s}   bias(out>0): {'none':>10s} {'per acc 0.21n':>14s} {'once fitted':>12s} {'once 0.155n':>12s}")
+    for r in once:
+        print(f"{r[0]:44s} {r[1]:5d} {r[2]:7.3f} {r[3]:7.4f}                {r[4]:+10.2e} {r[5]:+14.2e} {r[6]:+12.2e} {r[7]:+12.2e}")
+    per = np.array([k / n for _, n, k in rows])
+    print(f"kappa per MMA: mean {per.mean():.4f}, min {per.min():.4f}, max {per.max():.4f}")
+
+
+if __name__ == "__main__":
+    main()
