@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsnb200.so")
 SNB_OK, SNB_ERR_INVALID, SNB_ERR_MODEL, SNB_ERR_CUDA, SNB_ERR_NOMEM, SNB_ERR_BUSY = 0, -1, -2, -3, -4, -5
 PREC_FP32, PREC_TC_F16X2 = 0, 1
 FLAG_DEFER_WEIGHTS = 1024
+FLAG_NO_HEADFUSE = 64
 FLAG_KEEP_STAGES, FLAG_NO_GRAPH, FLAG_CORRECT_CHROMA, FLAG_NO_TENSOR, FLAG_NO_FUSE, FLAG_NO_STREAM, FLAG_NO_HBMCONV, FLAG_NO_COALESCE = 1, 2, 4, 8, 16, 32, 128, 256
 LAYOUT_NCHW, TENSOR_S8, TENSOR_S32 = 2, 1, 3
 

@@ -39,8 +39,10 @@ static void worker_main(snb_ctx* c);
 // one eager pass over zeros: sets kernel attributes outside graph capture and surfaces launch errors at init
 static int warm_up(snb_ctx* c) {
   cudaMemsetAsync(c->d_in, 0, c->in_bytes * c->maxB, c->stream);
-  launch_pre_s8(c->d_in, c->img, c->maxB, c->H, c->W, c->stream);
-  int r = run_plan(c, c->maxB, c->stream, false);
+  if (!c->direct_io) launch_pre_s8(c->d_in, c->img, c->maxB, c->H, c->W, c->stream);
+  IoPtrs io;
+  io.s8 = c->d_in; io.q = c->d_out;
+  int r = run_plan(c, c->maxB, io, c->stream, false);
   if (r == SNB_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) {
     snprintf(c->err, sizeof(c->err), "warm-up pass failed: %s", cudaGetErrorString(cudaGetLastError()));
     r = SNB_ERR_CUDA;
@@ -204,7 +206,7 @@ int snb_set_weights(snb_ctx* c, const void* blob, uint64_t bytes, int is_device)
   if (r != SNB_OK) { snprintf(g_err, sizeof(g_err), "%s", c->err); return r; }     // the old model stays installed
   sync_last_pass(c);                                   // no pass may still read the buffers replaced below
   // device pointers baked into the plan/graphs change: rebuild both
-  for (auto& g : c->graphs) cudaGraphExecDestroy(g.second);
+  for (auto& g : c->graphs) { cudaGraphExecDestroy(g.second.exec); if (g.second.graph) cudaGraphDestroy(g.second.graph); }
   c->graphs.clear();
   c->wts = std::move(wts); c->blob_K = blob_K;
   r = upload_weights(c);
@@ -267,31 +269,44 @@ int snb_get_model_input_size(const snb_ctx* c, int32_t idx, int32_t* w, int32_t*
   return SNB_OK;
 }
 
-// one chunk (<= maxB pairs) on stream st; inputs already in c->d_in / c->img as selected by `src`
-static int run_chunk(snb_ctx* c, int B, const int8_t* d_in, const uint8_t* d_frames, int32_t* d_out, cudaStream_t st) {
-  cudaError_t e;
+// one chunk (<= maxB pairs) on stream st.  d_in: the s8 tensor (input of the pass; with d_frames != nullptr it is the buffer
+// the NV12 kernel writes the tensor into first).
+static int run_chunk(snb_ctx* c, int B, int8_t* d_in, const uint8_t* d_frames, int32_t* d_out, cudaStream_t st) {
+  cudaError_t e = cudaSuccess;
   if (c->broken) { snprintf(c->err, sizeof(c->err), "no model installed: the last snb_set_weights failed"); return SNB_ERR_MODEL; }
   // the scratch set is shared by every pass: order this pass behind the previous one when that ran on another stream
   if (c->last_stream && c->last_stream != st && cudaStreamWaitEvent(st, c->ev_last, 0) != cudaSuccess) {
     snprintf(c->err, sizeof(c->err), "cudaStreamWaitEvent: %s", cudaGetErrorString(cudaGetLastError()));
     return SNB_ERR_CUDA;
   }
-  if (d_frames)
-    e = launch_pre_nv12(d_frames, c->img, nullptr, B, c->H, c->W, (c->cfg.flags & SNB_FLAG_CORRECT_CHROMA) ? 1 : 0, st);
-  else
+  const int correct = (c->cfg.flags & SNB_FLAG_CORRECT_CHROMA) ? 1 : 0;
+  IoPtrs io;
+  io.s8 = d_in; io.q = d_out;
+  if (c->direct_io) {
+    // the pass reads the s8 tensor and writes the s32 tensor itself; camera frames become that tensor first (P1-P3 on the GPU)
+    if (d_frames) e = launch_pre_nv12(d_frames, Tens(), d_in, B, c->H, c->W, correct, st);
+  } else if (d_frames) {
+    e = launch_pre_nv12(d_frames, c->img, nullptr, B, c->H, c->W, correct, st);
+  } else {
     e = launch_pre_s8(d_in, c->img, B, c->H, c->W, st);
+  }
   if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "pre: %s", cudaGetErrorString(e)); return SNB_ERR_CUDA; }
-  int r = run_plan(c, B, st, !(c->cfg.flags & (SNB_FLAG_NO_GRAPH | SNB_FLAG_KEEP_STAGES)));
+  int r = run_plan(c, B, io, st, !(c->cfg.flags & (SNB_FLAG_NO_GRAPH | SNB_FLAG_KEEP_STAGES)));
   if (r != SNB_OK) return r;
-  Plane d = c->disp_final; d.n = B;
-  e = launch_post_quant(d, d_out, c->H, c->W, c->qmul, st);
-  if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "post: %s", cudaGetErrorString(e)); return SNB_ERR_CUDA; }
+  if (!c->direct_io) {
+    Plane d = c->disp_final; d.n = B;
+    e = launch_post_quant(d, d_out, c->H, c->W, c->qmul, st);
+    if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "post: %s", cudaGetErrorString(e)); return SNB_ERR_CUDA; }
+  }
   cudaEventRecord(c->ev_last, st);
   c->last_stream = st;
   c->last_B = B;
   ++c->n_passes;
   return SNB_OK;
 }
+
+// kernels of this library per pass: the plan, plus the pre / post kernels where the pass does not contain them
+static int launches_per_pass(const snb_ctx* c, bool nv12) { return (int)c->ops.size() + (c->direct_io ? (nv12 ? 1 : 0) : 2); }
 
 static int infer_host(snb_ctx* c, const int8_t* in, const uint8_t* frames, int32_t* out, int batch) {
   if (!c || (!in && !frames) || !out || batch < 1) return fail(c, SNB_ERR_INVALID, "snb_infer: bad arguments");
@@ -315,7 +330,7 @@ static int infer_host(snb_ctx* c, const int8_t* in, const uint8_t* frames, int32
   const double t1 = now_s();
   c->stat.gpu_ms = gpu_ms;
   c->stat.infer_time_ms = (int)((t1 - t0) * 1e3 + 0.5);
-  c->stat.kernel_launches = (int)c->ops.size() + 2;
+  c->stat.kernel_launches = launches_per_pass(c, frames != nullptr);
   c->fps_in += batch; c->fps_out += batch;
   c->stat.fps_updated = 0;
   if (t1 - c->fps_t0 >= 1.0) {     // dnn_node refreshes its fps statistics about once a second
@@ -341,7 +356,7 @@ int snb_infer_device(snb_ctx* c, const int8_t* d_in, int32_t* d_out, int32_t bat
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
   for (int b0 = 0; b0 < batch; b0 += c->maxB) {
     const int B = std::min(c->maxB, batch - b0);
-    int r = run_chunk(c, B, d_in + (size_t)b0 * c->in_bytes, nullptr, d_out + (size_t)b0 * c->H * c->W, st);
+    int r = run_chunk(c, B, const_cast<int8_t*>(d_in) + (size_t)b0 * c->in_bytes, nullptr, d_out + (size_t)b0 * c->H * c->W, st);
     if (r != SNB_OK) { snprintf(g_err, sizeof(g_err), "%s", c->err); return r; }
   }
   if (!cuda_stream) CK(c, cudaStreamSynchronize(st));
@@ -386,7 +401,7 @@ int snb_pre_nv12_gpu(snb_ctx* c, const uint8_t* frames, int32_t batch, int8_t* s
   for (int b0 = 0; b0 < batch; b0 += c->maxB) {
     const int B = std::min(c->maxB, batch - b0);
     CK(c, cudaMemcpyAsync(c->d_frames, frames + (size_t)b0 * c->frame_bytes, c->frame_bytes * B, cudaMemcpyHostToDevice, st));
-    cudaError_t e = launch_pre_nv12(c->d_frames, c->img, c->d_in, B, c->H, c->W, (c->cfg.flags & SNB_FLAG_CORRECT_CHROMA) ? 1 : 0, st);
+    cudaError_t e = launch_pre_nv12(c->d_frames, c->direct_io ? Tens() : c->img, c->d_in, B, c->H, c->W, (c->cfg.flags & SNB_FLAG_CORRECT_CHROMA) ? 1 : 0, st);
     if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "pre_nv12: %s", cudaGetErrorString(e)); return SNB_ERR_CUDA; }
     CK(c, cudaMemcpyAsync(s8_out + (size_t)b0 * c->in_bytes, c->d_in, c->in_bytes * B, cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
@@ -503,29 +518,38 @@ int snb_profile_pass(snb_ctx* c, int32_t batch, snb_kernel_time* out, int32_t ca
   if (c->broken) return fail(c, SNB_ERR_MODEL, "no model installed");
   CK(c, cudaSetDevice(c->cfg.device));
   cudaStream_t st = c->stream;
-  const int n = (int)c->ops.size() + 2;
+  sync_last_pass(c);
+  const bool wrap = !c->direct_io;                      // the older pipeline: pre_s8 before and post_quant after the plan
+  const int nops = (int)c->ops.size(), n = nops + (wrap ? 2 : 0), o0 = wrap ? 1 : 0;
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& e : ev) cudaEventCreate(&e);
+  IoPtrs io;
+  io.s8 = c->d_in; io.q = c->d_out;
   cudaEventRecord(ev[0], st);
-  launch_pre_s8(c->d_in, c->img, batch, c->H, c->W, st);
-  cudaEventRecord(ev[1], st);
-  for (int i = 0; i < (int)c->ops.size(); ++i) {
-    cudaError_t e = c->ops[i].fn(batch, st);
-    if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "%s: %s", c->ops[i].name.c_str(), cudaGetErrorString(e)); return SNB_ERR_CUDA; }
-    cudaEventRecord(ev[i + 2], st);
+  if (wrap) {
+    launch_pre_s8(c->d_in, c->img, batch, c->H, c->W, st);
+    cudaEventRecord(ev[1], st);
   }
-  Plane d = c->disp_final; d.n = batch;
-  launch_post_quant(d, c->d_out, c->H, c->W, c->qmul, st);
-  cudaEventRecord(ev[n], st);
+  for (int i = 0; i < nops; ++i) {
+    cudaError_t e = c->ops[i].fn(batch, io, st);
+    if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "%s: %s", c->ops[i].name.c_str(), cudaGetErrorString(e)); return SNB_ERR_CUDA; }
+    cudaEventRecord(ev[o0 + i + 1], st);
+  }
+  if (wrap) {
+    Plane d = c->disp_final; d.n = batch;
+    launch_post_quant(d, c->d_out, c->H, c->W, c->qmul, st);
+    cudaEventRecord(ev[n], st);
+  }
   CK(c, cudaStreamSynchronize(st));
   for (int i = 0; i < n && i < cap; ++i) {
     memset(&out[i], 0, sizeof(out[i]));
-    const char* nm = i == 0 ? "pre_s8" : (i == n - 1 ? "post_quant" : c->ops[i - 1].name.c_str());
+    const bool is_pre = wrap && i == 0, is_post = wrap && i == n - 1;
+    const char* nm = is_pre ? "pre_s8" : (is_post ? "post_quant" : c->ops[i - o0].name.c_str());
     snprintf(out[i].name, sizeof(out[i].name), "%s", nm);
     cudaEventElapsedTime(&out[i].ms, ev[i], ev[i + 1]);
-    if (i > 0 && i < n - 1) { out[i].flops = c->ops[i - 1].flops * batch; out[i].bytes = c->ops[i - 1].bytes * batch; }
-    else if (i == 0) out[i].bytes = (double)batch * (c->in_bytes + 2.0 * c->Hp * c->Wp * 32);
-    else out[i].bytes = (double)batch * (4.0 * c->Hp * c->Wp + c->out_bytes);
+    if (is_pre) out[i].bytes = (double)batch * (c->in_bytes + 2.0 * c->Hp * c->Wp * 32);
+    else if (is_post) out[i].bytes = (double)batch * (4.0 * c->Hp * c->Wp + c->out_bytes);
+    else { out[i].flops = c->ops[i - o0].flops * batch; out[i].bytes = c->ops[i - o0].bytes * batch; }
   }
   for (auto& e : ev) cudaEventDestroy(e);
   return n;
@@ -549,7 +573,7 @@ static void retire_oldest(snb_ctx* c) {
     const double t1 = now_s();
     c->stat.gpu_ms = ms;
     c->stat.infer_time_ms = (int)((t1 - sl.t0) * 1e3 + 0.5);
-    c->stat.kernel_launches = (int)c->ops.size() + 2;
+    c->stat.kernel_launches = launches_per_pass(c, !sl.tasks.empty() && sl.tasks[0].frames != nullptr);
     c->fps_in += sl.batch; c->fps_out += sl.batch;
     c->stat.fps_updated = 0;
     if (t1 - c->fps_t0 >= 1.0) {

@@ -32,6 +32,12 @@ namespace snb {
 
 using namespace ptx;
 
+// weights of output slice cc: the first ccs - ccs2 slices belong to the main convolution, the rest to the second head
+__device__ __forceinline__ const __half* cs_wslice(const CsParams& p, int cc) {
+  const int na = p.ccs - p.ccs2;
+  return cc < na ? p.w + (size_t)cc * (p.w_bytes / 2) : p.w2 + (size_t)(cc - na) * (p.w_bytes / 2);
+}
+
 constexpr int CS_THREADS = 192;
 constexpr int CS_EPI_WARPS = 4;
 constexpr int CS_SLOTS = 5;                     // TMEM slots of the large configuration (the co-resident one uses 2)
@@ -70,7 +76,7 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
     while (u0 < p.total_units && cs_decode(p, u0).nr <= 0) u0 += gridDim.x;
     if (u0 < p.total_units) {
       mbar_expect_tx(w_full, p.w_bytes);
-      bulk_load(s_w, p.w + (size_t)cs_decode(p, u0).cc * (p.w_bytes / 2), p.w_bytes, w_full);
+      bulk_load(s_w, cs_wslice(p, cs_decode(p, u0).cc), p.w_bytes, w_full);
     }
   }
   if (warp == 1) { tmem_alloc(&tmem_slot, p.tmem_cols); tmem_relinquish(); }
@@ -98,7 +104,7 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
         if (lane == 0 && nw > 0) {                           // (the first slice was staged in the prologue)
           CS_WAIT(tw0, w_empty, (nw & 1) ^ 1);
           mbar_expect_tx(w_full, p.w_bytes);
-          bulk_load(s_w, p.w + (size_t)un.cc * (p.w_bytes / 2), p.w_bytes, w_full);
+          bulk_load(s_w, cs_wslice(p, un.cc), p.w_bytes, w_full);
         }
         cur_cc = un.cc; ++nw;
       }
@@ -214,28 +220,36 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
       const CsUnit un = cs_decode(p, u);
       if (un.nr <= 0) continue;
+      // which convolution this slice belongs to (second head: the 1x1 shortcut sharing the launch)
+      const int na = p.ccs - p.ccs2;
+      const bool h2 = un.cc >= na;
+      const int ccl = h2 ? un.cc - na : un.cc;
+      const float wsc = h2 ? p.wsc2 : p.wsc;
+      const int relu = h2 ? p.relu2 : p.relu, ncb_out = h2 ? p.ncb_out2 : p.ncb_out;
       if (un.cc != cur_cc) {
         // all four epilogue warps use the same 32 biases; a named barrier keeps the refill ordered within the group
         asm volatile("bar.sync 1, 128;" ::: "memory");
         // partial rows live in the accumulator domain (weights x 2^k): so does the bias; finished values are multiplied by 2^-k
-        if (threadIdx.x - 64 < 32) s_bias[threadIdx.x - 64] = (int)(threadIdx.x - 64) < p.nbias ? p.bias[un.cc * NCO + (threadIdx.x - 64)] / p.wsc : 0.f;
+        if (threadIdx.x - 64 < 32)
+          s_bias[threadIdx.x - 64] = (int)(threadIdx.x - 64) < (h2 ? p.nbias2 : p.nbias) ? (h2 ? p.bias2 : p.bias)[ccl * NCO + (threadIdx.x - 64)] / wsc : 0.f;
         asm volatile("bar.sync 1, 128;" ::: "memory");
         cur_cc = un.cc;
       }
       const int opx = un.x0 + m;
       const bool col_ok = opx < p.W;
-      // MMAs that accumulate into one TMEM accumulator of a job: (valid depth taps) x (16-channel chunks) x 3 kernel columns,
-      // x 3 when hi*hi, hi*lo and lo*hi share the accumulator; feeds the round-toward-zero compensation (common.cuh)
+      // MMAs that add non-zero products to one TMEM accumulator of a job: (valid depth taps) x (16-channel chunks) x kernel
+      // columns carrying weights, x 3 when hi*hi, hi*lo and lo*hi share the accumulator; feeds the round-toward-zero compensation
       const int ndz = min(un.d + p.kz - 1 - zpad, p.D - 1) - max(un.d - zpad, 0) + 1;
-      const float kn = p.rzk * (float)(ndz * p.nk16 * ((SPLIT || NCO == 16) ? 3 : 9));
+      const float kn = p.rzk * (float)(ndz * p.nk16 * (h2 ? p.taps2 : p.taps) * ((SPLIT || NCO == 16) ? 1 : 3));
       if constexpr (NCO == 32) {
-        const __half* res = static_cast<const __half*>(p.res.p);
-        __half* out = static_cast<__half*>(p.out.p);
+        const __half* res = h2 ? nullptr : static_cast<const __half*>(p.res.p);
+        const TV& ov = h2 ? p.out2 : p.out;
+        __half* out = static_cast<__half*>(ov.p);
         float a0[32], a1[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) a0[c] = a1[c] = 0.f;
-        const size_t o_base = (size_t)un.n * p.out.ss + ((size_t)(un.cc * 4) * p.D + un.d) * p.out.slice + (size_t)(opx / p.ostride) * 8;
-        const size_t r_base = (size_t)un.n * p.res.ss + ((size_t)(un.cc * 4) * p.D + un.d) * p.res.slice + (size_t)opx * 8;
+        const size_t o_base = (size_t)un.n * ov.ss + ((size_t)(ccl * 4) * p.D + un.d) * ov.slice + (size_t)(opx / p.ostride) * 8;
+        const size_t r_base = (size_t)un.n * p.res.ss + ((size_t)(ccl * 4) * p.D + un.d) * p.res.slice + (size_t)opx * 8;
         for (int j = 0; j < un.nr + 2; ++j) {
           const int row = un.c + d * (un.i0 - 2 + j);       // the (stride-1) output row this job completes
           const bool ok = col_ok && j >= 2 && row < p.H && (p.ostride == 1 || !((row | opx) & 1));
@@ -276,13 +290,13 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
           __syncwarp();
           if (lane == 0) mbar_arrive(&s_empty[ts_cur]);
           if (ok) {
-            __half* op = out + o_base + (size_t)(row / p.ostride) * p.out.ws * 8;
+            __half* op = out + o_base + (size_t)(row / p.ostride) * ov.ws * 8;
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb) {
-              if (cb >= p.ncb_out) continue;                 // Cout < 32: the slice's upper channel blocks do not exist
+              if (cb >= ncb_out) continue;                   // Cout < 32: the slice's upper channel blocks do not exist
               float g[8];
 #pragma unroll
-              for (int q = 0; q < 8; ++q) g[q] = rz_comp(f[cb * 8 + q], kn) * p.wsc;   // truncation loss back, out of the 2^k weight scale
+              for (int q = 0; q < 8; ++q) g[q] = rz_comp(f[cb * 8 + q], kn) * wsc;   // truncation loss back, out of the 2^k weight scale
               if (res) {
                 const __half2* h2 = reinterpret_cast<const __half2*>(&rh[cb]);
                 const __half2* l2 = reinterpret_cast<const __half2*>(&rl[cb]);
@@ -292,14 +306,14 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
                   g[2 * q] += a.x + b.x; g[2 * q + 1] += a.y + b.y;
                 }
               }
-              if (p.relu) {
+              if (relu) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) g[q] = fmaxf(g[q], 0.f);
               }
               uint4 oh, ol;
               cs_split8(g, oh, ol);
-              *reinterpret_cast<uint4*>(op + (size_t)cb * p.D * p.out.slice) = oh;
-              *reinterpret_cast<uint4*>(op + (size_t)cb * p.D * p.out.slice + p.out.lo) = ol;
+              *reinterpret_cast<uint4*>(op + (size_t)cb * p.D * ov.slice) = oh;
+              *reinterpret_cast<uint4*>(op + (size_t)cb * p.D * ov.slice + ov.lo) = ol;
             }
           }
         }
@@ -311,12 +325,26 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
         // was the epilogue's whole period (1.8 k cycles per job against ~0.5 k of MMAs at full resolution), so the loads
         // run RES_AHEAD jobs ahead of their use.
         constexpr int RES_AHEAD = 3;
-        struct ResRaw { unsigned short h, l; float f; };    // kept as loaded: converting would wait for the load
+        struct ResRaw { unsigned short h, l; float f, f1, f2, f3; };    // kept as loaded: converting would wait for the load
         ResRaw rq[RES_AHEAD];
+        // res_mode 3: the residual is the x2 bilinear upsample (PyTorch, align_corners = False) of the previous stage's
+        // disparity [n][H/2][W/2] - the same expression k_refine_head feeds conv_in with; the column weights are per thread
+        const int ch = p.H >> 1, cw = p.W >> 1;
+        const float sxr = fmaxf((opx + 0.5f) * 0.5f - 0.5f, 0.f);
+        const int rx0 = min((int)sxr, cw - 1), rx1 = min(rx0 + 1, cw - 1);
+        const float lx1 = sxr - (float)(int)sxr, lx0 = 1.f - lx1;
         auto res_load = [&](int j) -> ResRaw {
-          ResRaw q; q.h = 0; q.l = 0; q.f = 0.f;
+          ResRaw q; q.h = 0; q.l = 0; q.f = 0.f; q.f1 = q.f2 = q.f3 = 0.f;
           const int row = un.c + d * (un.i0 - 2 + j);
           if (!(col_ok && j >= 2 && j < un.nr + 2 && row < p.H)) return q;
+          if (p.res_mode == 3) {
+            const float sy = fmaxf((row + 0.5f) * 0.5f - 0.5f, 0.f);
+            const int y0 = (int)sy, y1 = min(y0 + 1, ch - 1);
+            const float* rp = p.res_plane + (size_t)un.n * ch * cw;
+            q.f = __ldg(rp + (size_t)y0 * cw + rx0); q.f1 = __ldg(rp + (size_t)y0 * cw + rx1);
+            q.f2 = __ldg(rp + (size_t)y1 * cw + rx0); q.f3 = __ldg(rp + (size_t)y1 * cw + rx1);
+            return q;
+          }
           if (p.res_mode == 1) {                            // channel 0 of a C8 split-fp16 tensor
             const unsigned short* rp = reinterpret_cast<const unsigned short*>(p.res.p) + (size_t)un.n * p.res.ss + ((size_t)row * p.res.ws + opx) * 8;
             q.h = __ldg(rp); q.l = __ldg(rp + p.res.lo);
@@ -345,10 +373,19 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
           if (lane == 0) mbar_arrive(&s_empty[ts]);
           if (++ts == (uint32_t)p.nslots) { ts = 0; fpar ^= 1; }
           if (ok) {
-            const float r = rr.f + (__half2float(__ushort_as_half(rr.h)) + __half2float(__ushort_as_half(rr.l)));
-            float f = fmaf(rz_comp(a0 + (v2[0] + (v2[1] + v2[2])), kn), p.wsc, r);   // hi*hi + (hi*lo + lo*hi), truncation loss back, out of the 2^k weight scale
+            float r;
+            if (p.res_mode == 3) {
+              const float sy = fmaxf((row + 0.5f) * 0.5f - 0.5f, 0.f);
+              const float ly1 = sy - (float)(int)sy, ly0 = 1.f - ly1;
+              r = ly0 * (lx0 * rr.f + lx1 * rr.f1) + ly1 * (lx0 * rr.f2 + lx1 * rr.f3);
+            } else {
+              r = rr.f + (__half2float(__ushort_as_half(rr.h)) + __half2float(__ushort_as_half(rr.l)));
+            }
+            float f = fmaf(rz_comp(a0 + (v2[0] + (v2[1] + v2[2])), kn), wsc, r);   // hi*hi + (hi*lo + lo*hi), truncation loss back, out of the 2^k weight scale
             if (p.relu) f = fmaxf(f, 0.f);
             p.out_plane[o] = f;
+            // the last conv_out also emits the model output tensor (stereonet_node.cpp:1033): s32 NCHW, cropped to the valid size
+            if (p.io.q && row < p.qH && opx < p.qW) p.io.q[((size_t)un.n * p.qH + row) * p.qW + opx] = __float2int_rn(f * p.qmul);
           }
           a0 = a1 + (v1[0] + (v1[1] + v1[2]));
           a1 = (v0[0] + (v0[1] + v0[2])) + bias;
@@ -400,6 +437,7 @@ cudaError_t conv_stream_plan(CsPlan* plan, const Tens& in, int cin, int cout, in
   CsParams& p = plan->p;
   p.in = view(in);
   p.D = in.d; p.H = in.h; p.W = in.w; p.dil = dil; p.kz = kz; p.nk16 = cin / 16; p.in_pad = in.pad;
+  p.taps = 3;
   p.nco = cout == 1 ? 16 : 32;
   p.ccs = cout == 1 ? 1 : (cout + 31) / 32;
   p.ncb_out = cout >= 32 ? 4 : cout / 8;
@@ -462,8 +500,16 @@ static cudaError_t cs_launch_t(CsParams p, int grid, size_t smem, cudaStream_t s
 }
 
 cudaError_t launch_conv_stream(const CsPlan& plan, int N, const void* w, int wlog2, const float* bias, const Tens* out, const Tens* res,
-                               float* out_plane, const float* res_plane, int res_c8_ch0, int relu, int ostride, cudaStream_t st) {
+                               float* out_plane, const float* res_plane, int res_c8_ch0, int relu, int ostride, cudaStream_t st,
+                               int res_plane_mode, const IoPtrs* io, int qH, int qW, float qmul, const CsHead2* head2) {
   CsParams p = plan.p;
+  if (head2) {                                      // the shortcut convolution of the same input rides along as extra output slices
+    p.ccs2 = (head2->cout + 31) / 32;
+    p.ccs += p.ccs2;
+    p.w2 = static_cast<const __half*>(head2->w); p.bias2 = head2->bias; p.out2 = view(*head2->out); p.relu2 = head2->relu;
+    p.taps2 = head2->ks == 1 ? 1 : 3; p.wsc2 = ldexpf(1.f, -head2->wlog2);
+    p.ncb_out2 = head2->cout >= 32 ? 4 : head2->cout / 8; p.nbias2 = head2->cout >= 32 ? 32 : head2->cout;
+  }
   p.ostride = ostride;
   p.N = N; p.w = static_cast<const __half*>(w); p.bias = bias; p.relu = relu;
   p.rzk = rz_unit();
@@ -471,7 +517,8 @@ cudaError_t launch_conv_stream(const CsPlan& plan, int N, const void* w, int wlo
   if (out) p.out = view(*out);
   p.res_mode = 0;
   if (res) { p.res = view(*res); p.res_mode = res_c8_ch0 ? 1 : 0; }
-  if (res_plane) { p.res_plane = res_plane; p.res_mode = 2; }
+  if (res_plane) { p.res_plane = res_plane; p.res_mode = res_plane_mode; }
+  if (io) { p.io = *io; p.qH = qH; p.qW = qW; p.qmul = qmul; }
   p.out_plane = out_plane;
   const int rc_max = cdiv(p.H, p.dil);
   const long columns = (long)p.ccs * N * p.D * p.strips * p.dil;

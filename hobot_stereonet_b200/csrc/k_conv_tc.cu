@@ -209,7 +209,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcConvParams p)
 #pragma unroll
         for (int c = 0; c < 16; ++c) acc[r][c] = 0.f;
 
-      const float kn = p.rzk * (p.cin8 ? 2.f : 3.f);      // MMAs per main chain: the kernel columns of one chunk (common.cuh rz_comp)
       for (int k16 = 0; k16 < p.nk16; ++k16) {
         for (int dz = 0; dz < p.kz; ++dz) {
           const int zin = tc.d + dz - zpad;
@@ -239,6 +238,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcConvParams p)
       // bias (+ residual) (+ ReLU), split into hi/lo, 16-byte stores (a warp writes 512 contiguous bytes)
       const long long cfin = clock64();
       const int co0 = tc.cc * NT + hf * 16;
+      {
+        // out of the accumulator domain, in place (keeps the finalisation below as lean as it was): the expected truncation loss
+        // of the tensor core's accumulate back (common.cuh rz_comp; 3 - or 2 - MMAs per TMEM chain), then the 2^-k weight scale
+        const float kn = p.rzk * (p.cin8 ? 2.f : 3.f), wsc = p.wsc;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int c = 0; c < 16; ++c) acc[r][c] = rz_comp(acc[r][c], kn) * wsc;
+      }
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int y = tc.ybase + r * p.dil;
@@ -249,7 +257,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcConvParams p)
             const size_t o = (size_t)tc.n * p.out.ss + ((size_t)cbo * p.D + tc.d) * p.out.slice + ((size_t)y * p.out.ws + x) * 8;
             float f[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = fmaf(rz_comp(acc[r][jb * 8 + j], kn), p.wsc, __ldg(p.bias + co0 + jb * 8 + j));   // truncation loss back, out of the 2^k weight scale
+            for (int j = 0; j < 8; ++j) f[j] = acc[r][jb * 8 + j] + __ldg(p.bias + co0 + jb * 8 + j);
             if (res) {
               const size_t ro = (size_t)tc.n * p.res.ss + ((size_t)cbo * p.D + tc.d) * p.res.slice + ((size_t)y * p.res.ws + x) * 8;
               const uint4 rh = __ldg(reinterpret_cast<const uint4*>(res + ro));

@@ -108,11 +108,18 @@ __global__ void k_pre_nv12(const uint8_t* __restrict__ frames, TV img, int8_t* _
       d[0] = sy; d[plane] = su; d[2 * plane] = sv;
     }
   }
-  St<T>::st8(img.p, (size_t)n * img.ss + ((size_t)y * img.ws + x) * 8, img.lo, v0);
+  if (img.p) St<T>::st8(img.p, (size_t)n * img.ss + ((size_t)y * img.ws + x) * 8, img.lo, v0);
 }
 
+// img.p == nullptr: only the s8 tensor is produced (the tensor-core path reads that tensor directly, there is no image tensor)
 cudaError_t launch_pre_nv12(const uint8_t* frames, Tens img, int8_t* s8, int B, int H, int W, int correct,
                             cudaStream_t st) {
+  if (!img.p) {
+    if (!s8) return cudaErrorInvalidValue;
+    const dim3 g(cdiv(W, 128), H, 2 * B);
+    launch_k(k_pre_nv12<__half>, g, 128, 0, st, frames, TV(), s8, B, H, W, H, W, correct);
+    return cudaGetLastError();
+  }
   const dim3 g(cdiv(img.w, 128), img.h, 2 * B);
   if (img.planes == 2)
     launch_k(k_pre_nv12<__half>, g, 128, 0, st, frames, view(img), s8, B, H, W, img.h, img.w, correct);

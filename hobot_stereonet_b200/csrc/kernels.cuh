@@ -22,13 +22,32 @@ cudaError_t launch_resblock_tc(const RbPlan& plan, int N, const void* wa, const 
 
 // k_conv_stream.cu — streaming tcgen05 convolution, weights resident in shared memory (M1, M3, M5)
 cudaError_t conv_stream_plan(CsPlan* plan, const Tens& in, int cin, int cout, int dil, int kz, int num_sms);
+// A second convolution of the same input served by the same launch (a BasicBlock's 1x1 shortcut next to its conv_a): same Cin, same
+// stride, C8 output, no residual.  Its weights are packed with cs_pack_weights like any other (1x1: the centre tap of a 3x3).
+struct CsHead2 { const void* w; int wlog2; const float* bias; const Tens* out; int cout, ks, relu; };
+// res_c8_ch0: 0 = C8 residual tensor `res`, 1 = channel 0 of `res`; res_plane_mode: 2 = fp32 plane like the output, 3 = x2 bilinear
+// upsample of the half-resolution fp32 plane.  q (optional, single-channel output only): the s32 model output tensor.
 cudaError_t launch_conv_stream(const CsPlan& plan, int N, const void* w, int wlog2, const float* bias, const Tens* out, const Tens* res,
-                               float* out_plane, const float* res_plane, int res_c8_ch0, int relu, int ostride, cudaStream_t st);
+                               float* out_plane, const float* res_plane, int res_c8_ch0, int relu, int ostride, cudaStream_t st,
+                               int res_plane_mode = 2, const IoPtrs* io = nullptr, int qH = 0, int qW = 0, float qmul = 0.f,
+                               const CsHead2* head2 = nullptr);
+// kernel size of the convolution a plan was made for (1: a 1x1 riding as the centre tap) - set by the caller after conv_stream_plan
+inline void conv_stream_set_taps(CsPlan* plan, int ks) { plan->p.taps = ks == 1 ? 1 : 3; }
 void cs_pack_weights(const float* W, int cout, int cin, int kz, int ks, int NCO, int wlog2, std::vector<__half>& out);
 
 // k_conv_hbm.cu — few-input-channel convolutions of the tensor path (firstconv.0, refinement conv_in): CUDA cores, weights in the constant bank
 void conv_first_pack(const float* W, const float* bias, int cin, ConvFirstParams* p);
 cudaError_t launch_conv_first(const ConvFirstParams& p, int N, cudaStream_t st);
+
+void conv_first_s8_pack(const float* W, const float* bias, ConvFirstS8Params* p);
+cudaError_t launch_conv_first_s8(ConvFirstS8Params p, const IoPtrs& io, int B, cudaStream_t st);
+// M4 + head of M5: (soft-argmin over D +) x2 bilinear upsample + left image from the s8 input + conv_in, one launch per stage
+void refine_head_pack(const float* W, const float* bias, RefineHeadParams* p);
+cudaError_t launch_refine_head(RefineHeadParams p, const IoPtrs& io, int B, cudaStream_t st);
+
+// stand-alone 1x1 convolutions (layer1.0's shortcut, lastconv.1): CUDA cores, one pixel per thread
+void conv1x1_pack(const float* W, int cout, int cin, int cbin, std::vector<float>& out);
+cudaError_t launch_conv1x1(Conv1x1Params p, int cout, int N, cudaStream_t st);
 
 // k_mem.cu — HBM-bound kernels
 // P3 tail on device: s8 NCHW [B,6,H,W] -> C8 [2B][1][Hp][Wp][8] (x/128; left n<B, right n>=B; ch 3..7 = 0)

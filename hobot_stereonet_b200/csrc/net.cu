@@ -235,6 +235,7 @@ struct Builder {
     // input channels as stored (blocks of 8, zero beyond cin) must be whole 16-channel chunks
     if (in.cb * 8 < cw.cin || (in.cb * 8) % 16) return false;
     if (conv_stream_plan(plan, in, in.cb * 8, cw.cout, cw.ks == 1 ? 1 : dil, cw.kz, c->num_sms) != cudaSuccess) return false;
+    conv_stream_set_taps(plan, cw.ks);
     // measured on config 2 (profiles/r01_final_opprof.txt): with the weights of one slice resident the streaming kernel
     // beats the staged k_conv_tc tiles wherever the slice fits (layer3/4 27 vs 30 us, head.filter.1-4 43 vs 50 us,
     // firstconv.1 26 vs 39, conv_out 41 vs 52, conv3d_alone 39 vs 64); head.filter.0 (221 KB) and lastconv.0 (295 KB) do not fit
@@ -264,10 +265,41 @@ struct Builder {
     op.flops = 2.0 * 2.0 * px * 32 * 32 * 9;
     op.bytes = 4.0 * px * 32 * (&res == &in || res.p == in.p ? 2 : 3);
     const int la = ia->second.wlog2, lb = ib->second.wlog2;
-    op.fn = [plan, nmul, wa, wb, la, lb, ba, bb](int B, cudaStream_t st) { return launch_resblock_tc(plan, nmul * B, wa, wb, la, lb, ba, bb, st); };
+    op.fn = [plan, nmul, wa, wb, la, lb, ba, bb](int B, const IoPtrs&, cudaStream_t st) { return launch_resblock_tc(plan, nmul * B, wa, wb, la, lb, ba, bb, st); };
     c->n_tc_convs += 2;
     c->ops.push_back(op);
     return out;
+  }
+
+  // conv_a (3x3, ReLU) and the 1x1 shortcut convolution of a BasicBlock read the same input: ONE streaming launch serves both,
+  // the shortcut as extra output slices (k_conv_stream second head).  false: not applicable, the caller emits two launches.
+  bool conv_with_shortcut(const std::string& name_a, const std::string& name_s, const Tens& in, int nmul, int stride, int dil, Tens* out_a,
+                          Tens* out_s) {
+    auto ia = c->convs.find(name_a), is = c->convs.find(name_s);
+    if (ia == c->convs.end() || is == c->convs.end() || (c->cfg.flags & SNB_FLAG_NO_FUSE)) return false;
+    ConvW& ca = ia->second; ConvW& cs = is->second;
+    if (ca.ks != 3 || cs.ks != 1 || ca.kz != 1 || cs.kz != 1 || ca.cin != cs.cin || ca.cout % 32 || cs.cout % 32) return false;
+    CsPlan splan;
+    if (!stream_ok(ca, in, stride, dil, &splan)) return false;
+    const int ho = (in.h + stride - 1) / stride, wo = (in.w + stride - 1) / stride;
+    const Tens oa = alloc(nmul, ca.cout, in.d, ho, wo, in.pad), os = alloc(nmul, cs.cout, in.d, ho, wo, in.pad);
+    const __half* wa = stream_weights(name_a, ca, 32);
+    const __half* ws = stream_weights(name_s, cs, 32);
+    if (!wa || !ws) return false;
+    const float* ba = ca.b; const float* bs = cs.b;
+    const int la = ca.wlog2, ls = cs.wlog2, couts = cs.cout;
+    Op op; op.name = name_a + " + " + name_s.substr(name_s.rfind('.') + 1) + " [tc-stream x2]";
+    const double px = (double)nmul * in.d * ho * wo;
+    op.flops = 2.0 * px * (ca.cout * ca.cin * 9.0 + cs.cout * cs.cin);
+    op.bytes = 4.0 * (nmul * (double)in.d * in.h * in.w * in.cb * 8 + px * (oa.cb + os.cb) * 8);
+    op.fn = [splan, nmul, wa, la, ba, oa, ws, ls, bs, os, couts, stride](int B, const IoPtrs&, cudaStream_t st) {
+      CsHead2 h2{ws, ls, bs, &os, couts, 1, 0};
+      return launch_conv_stream(splan, nmul * B, wa, la, ba, &oa, nullptr, nullptr, nullptr, 0, 1, stride, st, 2, nullptr, 0, 0, 0.f, &h2);
+    };
+    c->n_tc_convs += 2;
+    c->ops.push_back(op);
+    *out_a = oa; *out_s = os;
+    return true;
   }
 
   Tens conv(const std::string& name, const Tens& in, int nmul, int stride, int dil, bool relu, const Tens* res,
@@ -281,6 +313,18 @@ struct Builder {
     const double px = (double)nmul * in.d * ho * wo;
     op.flops = 2.0 * px * cw.cout * cw.cin * cw.ks * cw.ks * cw.kz;
     op.bytes = 4.0 * (nmul * (double)in.d * in.h * in.w * in.cb * 8 + px * out.cb * 8 * (res ? 2 : 1));
+    if (c->direct_io && cw.cout == 32 && cw.ks == 3 && cw.kz == 1 && cw.cin == 3 && stride == 2 && !res && dil == 1) {
+      // firstconv.0 straight from the s8 model input (k_conv_first_s8): `in` is only a geometry carrier here, it has no memory
+      ConvFirstS8Params fp{};
+      fp.out = view(out); fp.H = c->H; fp.W = c->W; fp.Ho = ho; fp.Wo = wo; fp.relu = relu ? 1 : 0;
+      conv_first_s8_pack(c->wts[name + ".weight"].data.data(), c->wts[name + ".bias"].data.data(), &fp);
+      op.fn = [fp](int B, const IoPtrs& io, cudaStream_t st) { return launch_conv_first_s8(fp, io, B, st); };
+      op.name += " [s8]";
+      op.io_bytes = (int)sizeof(ConvFirstS8Params);
+      op.bytes = 1.0 * nmul * 3.0 * c->H * c->W + 4.0 * px * out.cb * 8;       // three s8 planes per view in, C8 split out
+      c->ops.push_back(op);
+      return out;
+    }
     if (c->planes == 2 && !(c->cfg.flags & SNB_FLAG_NO_HBMCONV) && cw.cout == 32 && cw.ks == 3 && cw.kz == 1 && in.d == 1 && in.pad >= 1 && !res &&
         dil == 1 && cw.cin == 3 && stride == 2) {
       // the 3-channel image convolution: 13 FLOP per byte moved, CUDA cores with the weights in the constant bank (k_conv_hbm.cu);
@@ -288,9 +332,26 @@ struct Builder {
       ConvFirstParams fp{};
       fp.in = view(in); fp.out = view(out); fp.Ho = ho; fp.Wo = wo; fp.relu = relu ? 1 : 0; fp.stride = stride;
       conv_first_pack(c->wts[name + ".weight"].data.data(), c->wts[name + ".bias"].data.data(), cw.cin, &fp);
-      op.fn = [fp, nmul](int B, cudaStream_t st) { return launch_conv_first(fp, nmul * B, st); };
+      op.fn = [fp, nmul](int B, const IoPtrs&, cudaStream_t st) { return launch_conv_first(fp, nmul * B, st); };
       op.name += " [hbm]";
       op.bytes = (cw.cin == 3 ? 2.0 : 4.0) * nmul * (double)in.h * in.w * 8 + 4.0 * px * out.cb * 8;   // one channel block in, C8 split out
+      c->ops.push_back(op);
+      return out;
+    }
+    if (c->planes == 2 && !(c->cfg.flags & (SNB_FLAG_NO_TENSOR | SNB_FLAG_NO_HBMCONV)) && cw.ks == 1 && cw.kz == 1 && in.d == 1 && stride == 1 && !res &&
+        (cw.cout == 16 || cw.cout == 32) && in.cb * 8 >= cw.cin) {
+      // a 1x1 convolution on its own (layer1.0's shortcut, lastconv.1): far too little work for a tensor-pipe launch (k_conv1x1)
+      std::vector<float> packed;
+      conv1x1_pack(c->wts[name + ".weight"].data.data(), cw.cout, cw.cin, in.cb, packed);
+      float* dw = nullptr;
+      if (cudaMalloc(&dw, packed.size() * sizeof(float)) != cudaSuccess) { fail = true; return out; }
+      cudaMemcpy(dw, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice);
+      c->wallocs.push_back(dw);
+      Conv1x1Params qp{};
+      qp.in = view(in); qp.out = view(out); qp.wgt = dw; qp.bias = cw.b; qp.h = in.h; qp.w = in.w; qp.cbin = in.cb; qp.relu = relu ? 1 : 0;
+      const int cout = cw.cout;
+      op.fn = [qp, cout, nmul](int B, const IoPtrs&, cudaStream_t st) { return launch_conv1x1(qp, cout, nmul * B, st); };
+      op.name += " [1x1]";
       c->ops.push_back(op);
       return out;
     }
@@ -303,7 +364,7 @@ struct Builder {
       const Tens rt = res ? *res : Tens();
       const int rl = relu ? 1 : 0;
       const int wl = cw.wlog2;
-      op.fn = [splan, nmul, dw, wl, bias, out, has_res, rt, rl, stride](int B, cudaStream_t st) {
+      op.fn = [splan, nmul, dw, wl, bias, out, has_res, rt, rl, stride](int B, const IoPtrs&, cudaStream_t st) {
         return launch_conv_stream(splan, nmul * B, dw, wl, bias, &out, has_res ? &rt : nullptr, nullptr, nullptr, 0, rl, stride, st);
       };
       op.name += " [tc-stream]";
@@ -322,7 +383,7 @@ struct Builder {
       const Tens rt = res ? *res : Tens();
       const int sms = c->num_sms, rl = relu ? 1 : 0;
       const int wl = cw.wlog2;
-      op.fn = [plan, nmul, dw, wl, bias, has_res, rt, rl, sms](int B, cudaStream_t st) {
+      op.fn = [plan, nmul, dw, wl, bias, has_res, rt, rl, sms](int B, const IoPtrs&, cudaStream_t st) {
         return launch_conv_tc(plan, nmul * B, dw, wl, bias, has_res ? &rt : nullptr, rl, sms, st);
       };
       op.name += " [tc]";
@@ -338,13 +399,16 @@ struct Builder {
     p.ks = cw.ks; p.kz = cw.kz; p.stride = stride; p.dil = dil; p.relu = relu ? 1 : 0;
     p.half = c->planes == 2;
     const int cout = cw.cout;
-    op.fn = [p, nmul, cout](int B, cudaStream_t st) mutable { ConvParams q = p; q.N = nmul * B; return launch_conv_direct(q, cout, st); };
+    op.fn = [p, nmul, cout](int B, const IoPtrs&, cudaStream_t st) mutable { ConvParams q = p; q.N = nmul * B; return launch_conv_direct(q, cout, st); };
     ++c->n_direct_convs;
     c->ops.push_back(op);
     return out;
   }
 
-  Plane conv_to1(const std::string& name, const Tens& in, int dil, bool relu, const Tens* res_c8) {
+  // res_up: the residual is the x2 bilinear upsample of this half-resolution plane (direct_io refinement: no 4-channel input tensor
+  // exists to take it from); emit_q: this is the last conv_out and also writes the s32 model output
+  Plane conv_to1(const std::string& name, const Tens& in, int dil, bool relu, const Tens* res_c8, const Plane* res_up = nullptr,
+                 bool emit_q = false) {
     auto it = c->convs.find(name);
     if (it == c->convs.end()) { fail = true; snprintf(c->err, sizeof(c->err), "no weights for %s", name.c_str()); return Plane(); }
     ConvW& cw = it->second;
@@ -360,9 +424,14 @@ struct Builder {
       float* op_ = out.p;
       Op op; op.name = name + " [tc-stream]";
       const int wl = cw.wlog2;
-      op.fn = [splan, dw, wl, bias, op_, has_res, rt, rl](int B, cudaStream_t st) {
-        return launch_conv_stream(splan, B, dw, wl, bias, nullptr, has_res ? &rt : nullptr, op_, nullptr, 1, rl, 1, st);
+      const float* rup = res_up ? res_up->p : nullptr;
+      const int qH = c->H, qW = c->W;
+      const float qmul = c->qmul;
+      op.fn = [splan, dw, wl, bias, op_, has_res, rt, rl, rup, emit_q, qH, qW, qmul](int B, const IoPtrs& io, cudaStream_t st) {
+        return launch_conv_stream(splan, B, dw, wl, bias, nullptr, has_res ? &rt : nullptr, op_, rup, 1, rl, 1, st, 3, emit_q ? &io : nullptr, qH, qW,
+                                  qmul);
       };
+      if (emit_q) { op.io_bytes = (int)sizeof(CsParams); op.name += " [+s32 out]"; }
       const double px = (double)in.d * in.h * in.w;
       op.flops = 2.0 * px * cw.cin * 9 * cw.kz;
       op.bytes = 4.0 * (px * in.cb * 8 + px * (res_c8 ? 2 : 1));
@@ -370,6 +439,7 @@ struct Builder {
       c->ops.push_back(op);
       return out;
     }
+    if (res_up || emit_q) { fail = true; snprintf(c->err, sizeof(c->err), "%s: the fused refinement path needs the streaming kernel", name.c_str()); return out; }
     ConvTo1Params p{};
     p.in = view(in); p.out = out.p; p.w = cw.w; p.bias = cw.b0;
     p.res_c8 = res_c8 ? 1 : 0;
@@ -377,7 +447,7 @@ struct Builder {
     p.CBin = in.cb; p.D = in.d; p.H = in.h; p.W = in.w; p.kz = cw.kz; p.dil = dil; p.relu = relu ? 1 : 0;
     p.half = c->planes == 2;
     Op op; op.name = name;
-    op.fn = [p](int B, cudaStream_t st) { ConvTo1Params q = p; q.N = B; return launch_conv_to1(q, st); };
+    op.fn = [p](int B, const IoPtrs&, cudaStream_t st) { ConvTo1Params q = p; q.N = B; return launch_conv_to1(q, st); };
     const double px = (double)in.d * in.h * in.w;
     op.flops = 2.0 * px * cw.cin * 9 * cw.kz;
     op.bytes = 4.0 * (px * in.cb * 8 + px * (res_c8 ? 2 : 1));
@@ -392,15 +462,25 @@ int build_plan(snb_ctx* c) {
   c->arena.reuse = !(c->cfg.flags & SNB_FLAG_KEEP_STAGES);
   c->planes = c->cfg.precision == SNB_PREC_TC_F16X2 ? 2 : 1;
   c->n_tc_convs = c->n_direct_convs = 0;
+  // Tensor-core path: the kernels of the pass read the s8 model input themselves (firstconv.0, the refinement heads) and the
+  // last conv_out writes the s32 model output: no image tensor, no pre-process / post-process launch.  SNB_FLAG_NO_HEADFUSE
+  // (and the other diagnostic paths) keep the older pipeline: pre kernel -> C8 image -> ... -> soft-argmin, refine_in, conv_in.
+  c->direct_io = c->planes == 2 && !(c->cfg.flags & (SNB_FLAG_NO_TENSOR | SNB_FLAG_NO_STREAM | SNB_FLAG_NO_HBMCONV | SNB_FLAG_NO_HEADFUSE));
   Builder b{c, c->maxB};
   const int K = c->K, D = c->D, Hp = c->Hp, Wp = c->Wp, h = c->h, w = c->w;
 
-  // input image, C8 [2B][1][Hp][Wp][8]; the pre-process op is issued by the caller (s8 or NV12 source)
-  // 16 stored channels (3 real) on the tensor-core path: firstconv.0 consumes whole 16-channel K chunks
-  c->img = b.alloc(2, c->planes == 2 ? 16 : 3, 1, Hp, Wp, PAD_BACKBONE);
-  c->img.c = 3;
-  Tens img = c->img;
-  b.tap("img", img, 2);
+  Tens img;
+  if (c->direct_io) {
+    c->img = Tens();                     // geometry only: firstconv.0 reads the s8 tensor
+    img.n = 2 * c->maxB; img.c = 3; img.cb = 1; img.h = Hp; img.w = Wp; img.planes = 2; img.pad = PAD_BACKBONE;
+  } else {
+    // input image, C8 [2B][1][Hp][Wp][8]; the pre-process op is issued by the caller (s8 or NV12 source)
+    // 16 stored channels (3 real) on the tensor-core path: firstconv.0 consumes whole 16-channel K chunks
+    c->img = b.alloc(2, c->planes == 2 ? 16 : 3, 1, Hp, Wp, PAD_BACKBONE);
+    c->img.c = 3;
+    img = c->img;
+    b.tap("img", img, 2);
+  }
 
   // ---- M1 siamese backbone (left and right batched as n = 2B) ----
   Tens x = b.conv("backbone.firstconv.0", img, 2, 2, 1, true, nullptr);
@@ -418,14 +498,20 @@ int build_plan(snb_ctx* c) {
       const int s = bi == 0 ? strides[li - 1] : 1, dil = li == 4 ? 2 : 1;
       Tens sc = x;
       const bool ds = bi == 0 && li <= 3;
-      if (ds) sc = b.conv(p + ".downsample", x, 2, s, 1, false, nullptr);
+      const bool fused_block = s == 1 && b.block_fusable(p, x, dil);
+      Tens a;
+      bool have_a = false;
+      if (ds) {
+        if (!fused_block && b.conv_with_shortcut(p + ".conv_a", p + ".downsample", x, 2, s, dil, &a, &sc)) have_a = true;
+        else sc = b.conv(p + ".downsample", x, 2, s, 1, false, nullptr);
+      }
       Tens o;
-      if (s == 1 && b.block_fusable(p, x, dil)) {
+      if (fused_block) {
         o = b.resblock(p, x, 2, dil, sc);
       } else {
         const bool last = bi == LAYER_BLOCKS[li - 1] - 1;
         const Tens* dst = (li == 3 && last) ? &gwc_l3 : (li == 4 && last) ? &gwc_l4 : nullptr;
-        Tens a = b.conv(p + ".conv_a", x, 2, s, dil, true, nullptr);
+        if (!have_a) a = b.conv(p + ".conv_a", x, 2, s, dil, true, nullptr);
         o = b.conv(p + ".conv_b", a, 2, 1, dil, true, &sc, dst);
         b.free(a);
       }
@@ -447,7 +533,7 @@ int build_plan(snb_ctx* c) {
   Tens vol = b.alloc(1, 64, D, h, w, PAD_BACKBONE);
   {
     Op op; op.name = "costvol";
-    op.fn = [=](int B, cudaStream_t st) { return launch_costvol(gwc, cat, vol, B, D, st); };
+    op.fn = [=](int B, const IoPtrs&, cudaStream_t st) { return launch_costvol(gwc, cat, vol, B, D, st); };
     op.flops = 2.0 * 256 * D * h * w;
     op.bytes = 4.0 * (2.0 * (256 + 16) * h * w + 64.0 * D * h * w);
     c->ops.push_back(op);
@@ -465,30 +551,48 @@ int build_plan(snb_ctx* c) {
   Plane cost = b.conv_to1("head.conv3d_alone", v, 1, false, nullptr); b.free(v);
   b.tap("cost", cost);
 
-  // ---- M4 soft-argmin ----
+  // ---- M4 soft-argmin + M5 edge-aware refinement x K ----
   Plane disp = b.palloc(1, h, w);
-  {
+  if (!c->direct_io) {
     Op op; op.name = "softargmin";
-    op.fn = [=](int B, cudaStream_t st) { Plane cc = cost; cc.n = B; return launch_softargmin(cc, disp, st); };
+    op.fn = [=](int B, const IoPtrs&, cudaStream_t st) { Plane cc = cost; cc.n = B; return launch_softargmin(cc, disp, st); };
     op.bytes = 4.0 * (D + 1.0) * h * w;
     c->ops.push_back(op);
+    b.free(cost);
   }
-  b.free(cost);
   b.tap("disp0", disp);
 
-  // ---- M5 edge-aware refinement x K ----
   for (int s = 0; s < K; ++s) {
     const std::string p = "head.refine." + std::to_string(s);
     const int hs = disp.h * 2, ws = disp.w * 2;
-    Tens rin = b.alloc(1, 4, 1, hs, ws, PAD_REFINE);
-    {
+    Tens rin, f;
+    if (c->direct_io) {
+      // one launch: (stage 0: soft-argmin over D ->) x2 bilinear(disp) || left image from the s8 input -> conv_in + ReLU (k_refine_head)
+      auto wi = c->wts.find(p + ".conv_in.weight"), bi = c->wts.find(p + ".conv_in.bias");
+      if (wi == c->wts.end() || bi == c->wts.end()) { b.fail = true; snprintf(c->err, sizeof(c->err), "no weights for %s.conv_in", p.c_str()); break; }
+      f = b.alloc(1, 32, 1, hs, ws, PAD_REFINE);
+      RefineHeadParams rp{};
+      rp.src = s == 0 ? cost.p : disp.p; rp.disp0 = disp.p; rp.out = view(f);
+      rp.D = D; rp.h = disp.h; rp.w = disp.w; rp.H = c->H; rp.W = c->W; rp.f = Hp / hs; rp.stage0 = s == 0 ? 1 : 0; rp.invD = 1.0f / D;
+      refine_head_pack(wi->second.data.data(), bi->second.data.data(), &rp);
+      Op op; op.name = p + (s == 0 ? ".head [softargmin+up+conv_in]" : ".head [up+conv_in]");
+      op.fn = [rp](int B, const IoPtrs& io, cudaStream_t st) { return launch_refine_head(rp, io, B, st); };
+      op.io_bytes = (int)sizeof(RefineHeadParams);
+      op.flops = 2.0 * hs * ws * 32 * 4 * 9;
+      // algorithmic HBM bytes: cost (stage 0) or coarse disparity in, the left image at this resolution (3 s8 planes), split-fp16 feature out
+      op.bytes = (s == 0 ? 4.0 * (D + 1.0) * disp.h * disp.w : 4.0 * disp.h * disp.w) + 3.0 * std::min((double)c->H * c->W, (double)hs * ws * (rp.f == 1 ? 1 : 4)) +
+                 4.0 * 32.0 * hs * ws;
+      c->ops.push_back(op);
+      if (s == 0) b.free(cost);
+    } else {
+      rin = b.alloc(1, 4, 1, hs, ws, PAD_REFINE);
       Op op; op.name = p + ".in";
       Plane dsrc = disp;
-      op.fn = [=](int B, cudaStream_t st) { return launch_refine_in(dsrc, img, rin, B, st); };
+      op.fn = [=](int B, const IoPtrs&, cudaStream_t st) { return launch_refine_in(dsrc, img, rin, B, st); };
       op.bytes = 4.0 * (disp.h * disp.w + 3.0 * hs * ws + 8.0 * hs * ws);
       c->ops.push_back(op);
+      f = b.conv(p + ".conv_in", rin, 1, 1, 1, true, nullptr);
     }
-    Tens f = b.conv(p + ".conv_in", rin, 1, 1, 1, true, nullptr);
     for (int bi = 0; bi < 6; ++bi) {
       const std::string q = p + ".blocks." + std::to_string(bi);
       Tens o;
@@ -502,8 +606,9 @@ int build_plan(snb_ctx* c) {
       b.free(f); f = o;
     }
     b.tap("refine" + std::to_string(s) + ".feat", f, 1);
-    Plane nd = b.conv_to1(p + ".conv_out", f, 1, true, &rin);
-    b.free(f); b.free(rin); b.free(disp);
+    Plane nd = c->direct_io ? b.conv_to1(p + ".conv_out", f, 1, true, nullptr, &disp, s == K - 1) : b.conv_to1(p + ".conv_out", f, 1, true, &rin);
+    b.free(f); if (!c->direct_io) b.free(rin);
+    b.free(disp);
     disp = nd;
     b.tap("disp" + std::to_string(s + 1), disp);
   }
@@ -515,33 +620,68 @@ int build_plan(snb_ctx* c) {
   return SNB_OK;
 }
 
-int run_plan(snb_ctx* c, int B, cudaStream_t st, bool use_graph) {
+// The pass for batch B on stream st, reading / writing the buffers in `io`.  With use_graph the pass is captured once per
+// (B, kind of entry) and replayed; a later call with other buffers re-points the few kernels that touch them
+// (cudaGraphExecKernelNodeSetParams on the nodes recorded at capture: CPU work only, nothing is added on the stream).
+int run_plan(snb_ctx* c, int B, const IoPtrs& io, cudaStream_t st, bool use_graph) {
   if (use_graph) {
-    auto it = c->graphs.find(B);
+    const int key = 2 * B + (io.frames ? 1 : 0);
+    auto it = c->graphs.find(key);
     if (it == c->graphs.end()) {
+      GraphEntry ge;
       cudaGraph_t g = nullptr;
       if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return SNB_ERR_CUDA;
       cudaError_t e = cudaSuccess;
-      for (auto& op : c->ops) { e = op.fn(B, st); if (e != cudaSuccess) break; }
+      std::vector<std::pair<cudaGraphNode_t, int>> io_nodes;
+      for (auto& op : c->ops) {
+        e = op.fn(B, io, st);
+        if (e != cudaSuccess) break;
+        if (op.io_bytes > 0) {                 // the node just captured = the stream's only dependency now
+          cudaStreamCaptureStatus status; const cudaGraphNode_t* deps = nullptr; size_t ndeps = 0;
+          e = cudaStreamGetCaptureInfo(st, &status, nullptr, nullptr, &deps, &ndeps);
+          if (e != cudaSuccess || status != cudaStreamCaptureStatusActive || ndeps != 1) { if (e == cudaSuccess) e = cudaErrorUnknown; break; }
+          io_nodes.push_back({deps[0], op.io_bytes});
+        }
+      }
       cudaError_t e2 = cudaStreamEndCapture(st, &g);
       if (e != cudaSuccess || e2 != cudaSuccess) {
         snprintf(c->err, sizeof(c->err), "graph capture failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
         if (g) cudaGraphDestroy(g);
         return SNB_ERR_CUDA;
       }
-      cudaGraphExec_t ge = nullptr;
-      if (cudaGraphInstantiate(&ge, g, 0) != cudaSuccess) { cudaGraphDestroy(g); return SNB_ERR_CUDA; }
-      cudaGraphDestroy(g);
-      it = c->graphs.emplace(B, ge).first;
+      for (auto& pr : io_nodes) {
+        std::unique_ptr<GraphEntry::IoNode> n(new GraphEntry::IoNode());
+        n->node = pr.first;
+        if (cudaGraphKernelNodeGetParams(pr.first, &n->kp) != cudaSuccess || !n->kp.kernelParams) { cudaGraphDestroy(g); return SNB_ERR_CUDA; }
+        n->args.assign(static_cast<const char*>(n->kp.kernelParams[0]), static_cast<const char*>(n->kp.kernelParams[0]) + pr.second);
+        n->argv[0] = n->args.data();
+        n->kp.kernelParams = n->argv; n->kp.extra = nullptr;
+        ge.nodes.push_back(std::move(n));
+      }
+      if (cudaGraphInstantiate(&ge.exec, g, 0) != cudaSuccess) { cudaGraphDestroy(g); return SNB_ERR_CUDA; }
+      ge.graph = g;
+      ge.io = io;
+      it = c->graphs.emplace(key, std::move(ge)).first;
     }
-    if (cudaGraphLaunch(it->second, st) != cudaSuccess) {
+    GraphEntry& ge = it->second;
+    if (ge.io.s8 != io.s8 || ge.io.q != io.q || ge.io.frames != io.frames) {
+      for (auto& n : ge.nodes) {
+        memcpy(n->args.data(), &io, sizeof(IoPtrs));       // IoPtrs is the first member of every io kernel's parameter struct
+        if (cudaGraphExecKernelNodeSetParams(ge.exec, n->node, &n->kp) != cudaSuccess) {
+          snprintf(c->err, sizeof(c->err), "cudaGraphExecKernelNodeSetParams: %s", cudaGetErrorString(cudaGetLastError()));
+          return SNB_ERR_CUDA;
+        }
+      }
+      ge.io = io;
+    }
+    if (cudaGraphLaunch(ge.exec, st) != cudaSuccess) {
       snprintf(c->err, sizeof(c->err), "cudaGraphLaunch: %s", cudaGetErrorString(cudaGetLastError()));
       return SNB_ERR_CUDA;
     }
     return SNB_OK;
   }
   for (auto& op : c->ops) {
-    cudaError_t e = op.fn(B, st);
+    cudaError_t e = op.fn(B, io, st);
     if (e != cudaSuccess) {
       snprintf(c->err, sizeof(c->err), "%s: %s", op.name.c_str(), cudaGetErrorString(e));
       return SNB_ERR_CUDA;
@@ -551,7 +691,7 @@ int run_plan(snb_ctx* c, int B, cudaStream_t st, bool use_graph) {
 }
 
 void free_ctx(snb_ctx* c) {
-  for (auto& g : c->graphs) cudaGraphExecDestroy(g.second);
+  for (auto& g : c->graphs) { cudaGraphExecDestroy(g.second.exec); if (g.second.graph) cudaGraphDestroy(g.second.graph); }
   c->graphs.clear();
   c->arena.release_all();
   for (void* p : c->wallocs) cudaFree(p);

@@ -6,6 +6,7 @@
 #include <deque>
 #include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -32,9 +33,20 @@ struct ConvW {             // device-resident, kernel-specific packing of one co
 
 struct Op {
   std::string name;
-  std::function<cudaError_t(int B, cudaStream_t)> fn;
+  std::function<cudaError_t(int B, const IoPtrs& io, cudaStream_t)> fn;
   double flops = 0;        // algorithmic FLOPs per stereo pair
   double bytes = 0;        // algorithmic HBM bytes per stereo pair
+  int io_bytes = 0;        // > 0: the kernel reads / writes the call's own buffers; = sizeof its parameter struct, IoPtrs first
+};
+
+// A captured pass (one per batch size) and what is needed to point it at another call's buffers without re-capturing:
+// the kernel nodes whose parameter struct starts with an IoPtrs, each with a private copy of that struct.
+struct GraphEntry {
+  cudaGraph_t graph = nullptr;                 // kept: node handles are only valid while their graph lives
+  cudaGraphExec_t exec = nullptr;
+  IoPtrs io;                                   // what the nodes currently point at
+  struct IoNode { cudaGraphNode_t node; cudaKernelNodeParams kp; std::vector<char> args; void* argv[1]; };
+  std::vector<std::unique_ptr<IoNode>> nodes;
 };
 
 struct Stage {             // named tap for snb_debug_read
@@ -107,7 +119,8 @@ struct snb_ctx {
   uint8_t* d_frames = nullptr;         // NV12 frames [maxB][H*3/2][2W]
   size_t in_bytes = 0, out_bytes = 0, frame_bytes = 0;   // per pair
 
-  std::map<int, cudaGraphExec_t> graphs;   // by batch
+  std::map<int, snb::GraphEntry> graphs;   // by batch (x2 + 1 for the camera-frame entry: its pass starts with the NV12 kernel)
+  bool direct_io = false;              // tensor-core path: kernels of the pass read the s8 input / write the s32 output themselves (no image tensor, no pre / post launch)
   int last_B = 0;
   uint64_t n_passes = 0;               // whole-network passes launched so far (snb_get_pass_count)
 
@@ -132,6 +145,6 @@ namespace snb {
 int parse_blob(const void* blob, size_t bytes, std::map<std::string, HostTensor>* out, int* blob_K, char* err, size_t errlen);
 int upload_weights(snb_ctx* c);
 int build_plan(snb_ctx* c);
-int run_plan(snb_ctx* c, int B, cudaStream_t st, bool use_graph);
+int run_plan(snb_ctx* c, int B, const IoPtrs& io, cudaStream_t st, bool use_graph);
 void free_ctx(snb_ctx* c);
 }  // namespace snb

@@ -49,6 +49,7 @@ enum {
   SNB_FLAG_NO_TENSOR = 8,     /* diagnostics: SNB_PREC_TC_F16X2 storage, but every convolution on the CUDA-core kernel */
   SNB_FLAG_NO_FUSE = 16,      /* diagnostics: residual blocks as two separate convolution launches */
   SNB_FLAG_NO_STREAM = 32,    /* diagnostics: tiled k_conv_tc / CUDA-core kernels instead of the streaming convolution */
+  SNB_FLAG_NO_HEADFUSE = 64,  /* diagnostics: the older glue - pre-process kernel -> C8 image tensor, soft-argmin / refine_in / conv_in / post-quantise as separate launches - instead of the fused refinement heads reading the s8 input directly */
   SNB_FLAG_NO_HBMCONV = 128,  /* diagnostics: firstconv.0 on the tcgen05 streaming kernel instead of k_conv_first (k_conv_hbm.cu) */
   SNB_FLAG_NO_COALESCE = 256, /* snb_infer_async: one pass per call even when max_batch > 1 (default: queued calls are merged into passes of up to max_batch pairs) */
   SNB_FLAG_DEFER_WEIGHTS = 1024  /* snb_create without a model: the weights arrive through snb_set_weights (multi-GPU init, snb_pool_create); until then every infer call returns SNB_ERR_MODEL */

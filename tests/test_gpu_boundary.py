@@ -47,7 +47,8 @@ def test_gpu_preprocess_byte_exact(built_lib, H, W, correct):
         rng = np.random.default_rng(H)
         frames = np.concatenate([_frames(H, W, 1, seed=60), rng.integers(0, 256, (1, H * 3 // 2, 2 * W), dtype=np.uint8)])
         want = _s8(frames, H, W, correct)
-    m = _model(H, W, K=3, D=4, max_batch=2, flags=capi.FLAG_KEEP_STAGES | (capi.FLAG_CORRECT_CHROMA if correct else 0))
+    # FLAG_NO_HEADFUSE: the pipeline variant that materialises the image tensor (the default path reads the s8 tensor directly)
+    m = _model(H, W, K=3, D=4, max_batch=2, flags=capi.FLAG_KEEP_STAGES | capi.FLAG_NO_HEADFUSE | (capi.FLAG_CORRECT_CHROMA if correct else 0))
     got = m.pre_nv12_gpu(frames)
     assert got.dtype == np.int8 and got.shape == want.shape
     assert (got == want).all()                                          # byte for byte against the oracle / golden bytes
@@ -61,9 +62,18 @@ def test_gpu_preprocess_byte_exact(built_lib, H, W, correct):
     assert (img[:, :, :H, :W] == ref).all()
     assert (img[:, :, H:, :] == 0).all() and (img[:, :, :, W:] == 0).all()
     # the s8 entry point writes the identical image
-    m.infer(want)
+    q_old = m.infer(want)
     assert (m.debug_read("img")[:, :, :H, :W] == ref).all()
     m.close()
+    # default path (no image tensor: firstconv.0 and the refinement heads read the s8 tensor): same bytes from the GPU pre-process,
+    # and the camera-frame entry gives the same output as the tensor entry
+    m = _model(H, W, K=3, D=4, max_batch=2, flags=capi.FLAG_CORRECT_CHROMA if correct else 0)
+    assert (m.pre_nv12_gpu(frames) == want).all()
+    q_new = m.infer(want)
+    assert (m.infer_nv12(frames) == q_new).all()
+    m.close()
+    px = lambda q: q.astype(np.float64) * arch.OUT_SCALE * arch.OUT_NORM
+    assert np.abs(px(q_new) - px(q_old)).mean() < 1e-3        # the two pipeline variants agree to the parity bar
 
 
 def test_nv12_async_matches_sync_and_keeps_order(built_lib):

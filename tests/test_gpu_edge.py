@@ -90,7 +90,7 @@ def test_tc_unfused_and_tiled_paths_agree(built_lib):
     cfg = arch.Config(64, 160, 3, 8)
     s8 = _s8(cfg, seed=700)
     ref = Oracle(cfg, weights.generate(cfg.K, seed=1234)).forward_px(s8)
-    for flags in (0, capi.FLAG_NO_FUSE, capi.FLAG_NO_STREAM, capi.FLAG_NO_FUSE | capi.FLAG_NO_STREAM, capi.FLAG_NO_GRAPH, capi.FLAG_NO_HBMCONV):
+    for flags in (0, capi.FLAG_NO_FUSE, capi.FLAG_NO_STREAM, capi.FLAG_NO_FUSE | capi.FLAG_NO_STREAM, capi.FLAG_NO_GRAPH, capi.FLAG_NO_HBMCONV, capi.FLAG_NO_HEADFUSE):
         m = _model(cfg, flags=flags)
         err = np.abs(_px(m.infer(s8))[:, 0] - ref)
         m.close()
