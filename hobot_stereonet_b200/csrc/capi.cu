@@ -283,8 +283,9 @@ static int run_chunk(snb_ctx* c, int B, int8_t* d_in, const uint8_t* d_frames, i
   IoPtrs io;
   io.s8 = d_in; io.q = d_out;
   if (c->direct_io) {
-    // the pass reads the s8 tensor and writes the s32 tensor itself; camera frames become that tensor first (P1-P3 on the GPU)
-    if (d_frames) e = launch_pre_nv12(d_frames, Tens(), d_in, B, c->H, c->W, correct, st);
+    // the pass reads the s8 tensor and writes the s32 tensor itself; camera frames become that tensor by the first kernel of
+    // the pass (P1-P3 on the GPU, inside the captured graph: run_plan)
+    io.frames = d_frames;
   } else if (d_frames) {
     e = launch_pre_nv12(d_frames, c->img, nullptr, B, c->H, c->W, correct, st);
   } else {
@@ -359,6 +360,7 @@ int snb_infer_device(snb_ctx* c, const int8_t* d_in, int32_t* d_out, int32_t bat
     int r = run_chunk(c, B, const_cast<int8_t*>(d_in) + (size_t)b0 * c->in_bytes, nullptr, d_out + (size_t)b0 * c->H * c->W, st);
     if (r != SNB_OK) { snprintf(g_err, sizeof(g_err), "%s", c->err); return r; }
   }
+  c->stat.kernel_launches = launches_per_pass(c, false);
   if (!cuda_stream) CK(c, cudaStreamSynchronize(st));
   return SNB_OK;
 }

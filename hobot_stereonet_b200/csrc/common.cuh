@@ -87,6 +87,12 @@ struct IoPtrs {
   const uint8_t* frames = nullptr;
 };
 
+struct PreNv12Params {   // k_pre_nv12: camera frames (io.frames) -> the s8 model input (io.s8) and, on the older pipeline, the C8 image
+  IoPtrs io;
+  TV img;                // p == nullptr: no image tensor
+  int B, H, W, Hp, Wp, correct;
+};
+
 struct ConvParams {
   TV in, out, res;       // res: residual added before the activation (same geometry as out) or p == nullptr
   const float* w; const float* bias;

@@ -72,14 +72,17 @@ cudaError_t launch_pre_s8(const int8_t* s8, Tens img, int B, int H, int W, cudaS
 // Restates stereonet_node.cpp:702-738 (L/R split), preprocess.h:128-155 (YUV420TOYUV444 incl. the
 // I420-indexing quirk on NV12 data) and preprocess.cpp:1032-1040 (x-128) in one pass.
 template <typename T>
-__global__ void k_pre_nv12(const uint8_t* __restrict__ frames, TV img, int8_t* __restrict__ s8, int B, int H, int W, int Hp,
-                           int Wp, int correct) {
+__global__ void k_pre_nv12(const PreNv12Params p) {
   pdl_trigger();
   pdl_wait();
+  const uint8_t* __restrict__ frames = p.io.frames;
+  int8_t* __restrict__ s8 = const_cast<int8_t*>(p.io.s8);       // this kernel PRODUCES the s8 tensor the rest of the pass reads
+  const TV img = p.img;
+  const int B = p.B, H = p.H, W = p.W;
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int n = blockIdx.z;
-  if (x >= Wp) return;
+  if (x >= p.Wp) return;
   const int b = n % B, view = n / B;
   float v0[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (x < W && y < H) {
@@ -87,7 +90,7 @@ __global__ void k_pre_nv12(const uint8_t* __restrict__ frames, TV img, int8_t* _
     const int pitch = 2 * W;
     const uint8_t yy = f[(size_t)y * pitch + x];
     uint8_t u, v;
-    if (correct) {
+    if (p.correct) {
       const uint8_t* row = f + (size_t)(H + (y >> 1)) * pitch;
       u = row[(x >> 1) * 2];
       v = row[(x >> 1) * 2 + 1];
@@ -114,17 +117,19 @@ __global__ void k_pre_nv12(const uint8_t* __restrict__ frames, TV img, int8_t* _
 // img.p == nullptr: only the s8 tensor is produced (the tensor-core path reads that tensor directly, there is no image tensor)
 cudaError_t launch_pre_nv12(const uint8_t* frames, Tens img, int8_t* s8, int B, int H, int W, int correct,
                             cudaStream_t st) {
+  PreNv12Params p{};
+  p.io.frames = frames; p.io.s8 = s8;
+  p.B = B; p.H = H; p.W = W; p.correct = correct;
   if (!img.p) {
     if (!s8) return cudaErrorInvalidValue;
-    const dim3 g(cdiv(W, 128), H, 2 * B);
-    launch_k(k_pre_nv12<__half>, g, 128, 0, st, frames, TV(), s8, B, H, W, H, W, correct);
+    p.Hp = H; p.Wp = W;
+    launch_k(k_pre_nv12<__half>, dim3(cdiv(W, 128), H, 2 * B), 128, 0, st, p);
     return cudaGetLastError();
   }
+  p.img = view(img); p.Hp = img.h; p.Wp = img.w;
   const dim3 g(cdiv(img.w, 128), img.h, 2 * B);
-  if (img.planes == 2)
-    launch_k(k_pre_nv12<__half>, g, 128, 0, st, frames, view(img), s8, B, H, W, img.h, img.w, correct);
-  else
-    launch_k(k_pre_nv12<float>, g, 128, 0, st, frames, view(img), s8, B, H, W, img.h, img.w, correct);
+  if (img.planes == 2) launch_k(k_pre_nv12<__half>, g, 128, 0, st, p);
+  else launch_k(k_pre_nv12<float>, g, 128, 0, st, p);
   return cudaGetLastError();
 }
 

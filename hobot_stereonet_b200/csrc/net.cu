@@ -633,15 +633,21 @@ int run_plan(snb_ctx* c, int B, const IoPtrs& io, cudaStream_t st, bool use_grap
       if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return SNB_ERR_CUDA;
       cudaError_t e = cudaSuccess;
       std::vector<std::pair<cudaGraphNode_t, int>> io_nodes;
+      auto note_io_node = [&](int bytes) {     // the node just captured = the stream's only dependency now
+        cudaStreamCaptureStatus status; const cudaGraphNode_t* deps = nullptr; size_t ndeps = 0;
+        cudaError_t ce = cudaStreamGetCaptureInfo(st, &status, nullptr, nullptr, &deps, &ndeps);
+        if (ce != cudaSuccess || status != cudaStreamCaptureStatusActive || ndeps != 1) return ce == cudaSuccess ? cudaErrorUnknown : ce;
+        io_nodes.push_back({deps[0], bytes});
+        return cudaSuccess;
+      };
+      if (io.frames && c->direct_io) {         // camera-frame entry: P1-P3 on the GPU is the first kernel of the pass
+        e = launch_pre_nv12(io.frames, Tens(), const_cast<int8_t*>(io.s8), B, c->H, c->W, (c->cfg.flags & SNB_FLAG_CORRECT_CHROMA) ? 1 : 0, st);
+        if (e == cudaSuccess) e = note_io_node((int)sizeof(PreNv12Params));
+      }
       for (auto& op : c->ops) {
-        e = op.fn(B, io, st);
         if (e != cudaSuccess) break;
-        if (op.io_bytes > 0) {                 // the node just captured = the stream's only dependency now
-          cudaStreamCaptureStatus status; const cudaGraphNode_t* deps = nullptr; size_t ndeps = 0;
-          e = cudaStreamGetCaptureInfo(st, &status, nullptr, nullptr, &deps, &ndeps);
-          if (e != cudaSuccess || status != cudaStreamCaptureStatusActive || ndeps != 1) { if (e == cudaSuccess) e = cudaErrorUnknown; break; }
-          io_nodes.push_back({deps[0], op.io_bytes});
-        }
+        e = op.fn(B, io, st);
+        if (e == cudaSuccess && op.io_bytes > 0) e = note_io_node(op.io_bytes);
       }
       cudaError_t e2 = cudaStreamEndCapture(st, &g);
       if (e != cudaSuccess || e2 != cudaSuccess) {
@@ -679,6 +685,10 @@ int run_plan(snb_ctx* c, int B, const IoPtrs& io, cudaStream_t st, bool use_grap
       return SNB_ERR_CUDA;
     }
     return SNB_OK;
+  }
+  if (io.frames && c->direct_io) {
+    cudaError_t e = launch_pre_nv12(io.frames, Tens(), const_cast<int8_t*>(io.s8), B, c->H, c->W, (c->cfg.flags & SNB_FLAG_CORRECT_CHROMA) ? 1 : 0, st);
+    if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "pre_nv12: %s", cudaGetErrorString(e)); return SNB_ERR_CUDA; }
   }
   for (auto& op : c->ops) {
     cudaError_t e = op.fn(B, io, st);

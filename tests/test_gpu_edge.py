@@ -110,8 +110,8 @@ def test_config3_shape_batch2_vs_oracle(built_lib):
 
 @pytest.mark.parametrize("H,W,D,B", [(540, 960, 192, 2), (375, 1242, 192, 2)])
 def test_high_disparity_full_size_properties(built_lib, H, W, D, B):
-    """BASELINE.json configs[3] / [4] shapes (D = 192): tensor-core path vs the exact fp32 GPU path, determinism,
-    batch invariance, range.  The CPU oracle is not run at this size (minutes per pair)."""
+    """BASELINE.json configs[3] / [4] shapes (D = 192): determinism, batch invariance, range, and the tensor-core path against
+    the exact fp32 GPU path at the flat 1e-3 px bar."""
     cfg = arch.Config(H, W, 3, D)
     s8 = _s8(cfg, seed=1100 + H, n=B)
     m = _model(cfg, max_batch=B)
@@ -120,16 +120,14 @@ def test_high_disparity_full_size_properties(built_lib, H, W, D, B):
     assert (m.infer(s8[1:2]) == q[1:2]).all()                         # a pair does not see its batch neighbour
     m.close()
     assert q.shape == (B, 1, H, W) and q.min() >= 0 and _px(q).max() < 2 * cfg.max_disp
+    # agreement with the exact-arithmetic fp32 CUDA path at the flat bar (both are checked against the CPU oracle at this size
+    # in tests/test_gpu_d192.py)
     mf = _model(cfg, tc=False, max_batch=1)
     qf = mf.infer(s8[:1])
     mf.close()
     err = np.abs(_px(q[:1]) - _px(qf))
     print(f"{H}x{W} D={D}: tensor-core vs fp32 path mean {err.mean():.3e} px, max {err.max():.3e} px")
-    # The network carries disparity normalised by max_disp, so absolute error scales with the range:
-    # north_star's 1e-3 px at config 2 (max_disp 192) is 5.2e-6 of the range; the same relative bar here (max_disp 1536,
-    # where one fp32 ulp of the output is already 9e-5 px and the two fp32 references differ by a few s32 steps).
-    scale = cfg.max_disp / 192.0
-    assert err.mean() <= EPE_BAR * scale and err.max() <= MAX_BAR * scale
+    assert err.mean() <= EPE_BAR and err.max() <= MAX_BAR
 
 
 def test_gpu_depth_and_colormap_bit_exact(built_lib):
