@@ -240,7 +240,8 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
       // MMAs that add non-zero products to one TMEM accumulator of a job: (valid depth taps) x (16-channel chunks) x kernel
       // columns carrying weights, x 3 when hi*hi, hi*lo and lo*hi share the accumulator; feeds the round-toward-zero compensation
       const int ndz = min(un.d + p.kz - 1 - zpad, p.D - 1) - max(un.d - zpad, 0) + 1;
-      const float kn = p.rzk * (float)(ndz * p.nk16 * (h2 ? p.taps2 : p.taps) * ((SPLIT || NCO == 16) ? 1 : 3));
+      const float kn = p.rzk * (float)(ndz * p.nk16 * (h2 ? p.taps2 : p.taps) * ((SPLIT || NCO == 16) ? 1 : 3)) *
+                       (NCO == 16 ? RZ_KAPPA_1CH_PER_MMA / RZ_KAPPA_PER_MMA : 1.f);
       if constexpr (NCO == 32) {
         const __half* res = h2 ? nullptr : static_cast<const __half*>(p.res.p);
         const TV& ov = h2 ? p.out2 : p.out;
