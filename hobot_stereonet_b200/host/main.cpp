@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <chrono>
 #include <fstream>
 #include <mutex>
 
@@ -47,6 +48,7 @@ int main(int argc, char** argv) {
     ++published;
   });
   const int n = (int)(all.size() / frame_bytes);
+  const auto t0 = std::chrono::steady_clock::now();
   for (int r = 0; r < repeat; ++r)
     for (int i = 0; i < n; ++i) {
       HbmMsg1080P msg;
@@ -55,6 +57,9 @@ int main(int argc, char** argv) {
       node.FeedImg(msg);
     }
   node.WaitAll();
+  const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   fprintf(stderr, "fed %d frame(s), published %d, dropped %d\n", n * repeat, published, node.dropped_frames());
+  fprintf(stderr, "%d GPU(s), %.3f s, %.1f frames/s end to end (FeedImg -> Run -> PostProcess -> publish callback)\n", node.device_count(),
+          secs, n * repeat / secs);
   return published + node.dropped_frames() == n * repeat ? 0 : 1;
 }
