@@ -372,14 +372,14 @@ def nv12_to_bgr(nv12: np.ndarray, w: int, h: int) -> np.ndarray:
 
 def jpeg_encode_nv12(nv12: np.ndarray, w: int, h: int, quality: int = 0) -> bytes:
     src = np.ascontiguousarray(nv12, np.uint8)
-    n = lib().snb_jpeg_encode_nv12(_ptr(src), w, h, quality, None, 0)
+    dst = np.empty(w * h * 3 + 4096, np.uint8)
+    n = lib().snb_jpeg_encode_nv12(_ptr(src), w, h, quality, _ptr(dst), dst.size)
     if n < 0:
         raise SnbError(int(n), "snb_jpeg_encode_nv12")
-    dst = np.empty(n, np.uint8)
-    n2 = lib().snb_jpeg_encode_nv12(_ptr(src), w, h, quality, _ptr(dst), n)
-    if n2 != n:
-        raise SnbError(int(n2), "snb_jpeg_encode_nv12")
-    return dst.tobytes()
+    if n > dst.size:                       # the call reports the size it needs and never writes past the buffer
+        dst = np.empty(n, np.uint8)
+        n = lib().snb_jpeg_encode_nv12(_ptr(src), w, h, quality, _ptr(dst), n)
+    return dst[:n].tobytes()
 
 
 def synthesize_weights(K: int, seed: int = 1234) -> bytes:

@@ -71,19 +71,26 @@ void build_huff(const uint8_t* bits, const uint8_t* vals, Huff* h) {
 
 struct BitWriter {
   uint8_t* dst; uint64_t cap, n = 0;
-  uint64_t acc = 0; int nbits = 0;
+  uint64_t acc = 0; int nbits = 0;          // the low `nbits` bits of acc are pending, most significant first
   bool overflow = false;
   void byte(uint8_t b) { if (n < cap) dst[n] = b; else overflow = true; ++n; }
   void put(uint32_t code, int len) {
     acc = (acc << len) | (code & ((1u << len) - 1)); nbits += len;
-    while (nbits >= 8) {
-      const uint8_t b = (uint8_t)(acc >> (nbits - 8));
-      byte(b);
-      if (b == 0xff) byte(0);               // byte stuffing
-      nbits -= 8;
+    if (nbits >= 32) {                        // flush four bytes at once; 0xFF bytes (rare) take the byte-stuffing path
+      const uint32_t w = (uint32_t)(acc >> (nbits - 32));
+      nbits -= 32;
+      if (n + 4 <= cap && !((w & ~(w + 0x01010101u)) & 0x80808080u)) {      // no byte of w is 0xFF
+        dst[n] = (uint8_t)(w >> 24); dst[n + 1] = (uint8_t)(w >> 16); dst[n + 2] = (uint8_t)(w >> 8); dst[n + 3] = (uint8_t)w;
+        n += 4;
+      } else {
+        for (int s = 24; s >= 0; s -= 8) { const uint8_t b = (uint8_t)(w >> s); byte(b); if (b == 0xff) byte(0); }
+      }
     }
   }
-  void flush() { if (nbits) put(0x7f, 8 - nbits); }
+  void flush() {
+    while (nbits >= 8) { const uint8_t b = (uint8_t)(acc >> (nbits - 8)); byte(b); if (b == 0xff) byte(0); nbits -= 8; }
+    if (nbits) { const uint8_t b = (uint8_t)(((acc << (8 - nbits)) | ((1u << (8 - nbits)) - 1)) & 0xff); byte(b); if (b == 0xff) byte(0); nbits = 0; }
+  }
   void u16(uint32_t v) { byte((uint8_t)(v >> 8)); byte((uint8_t)v); }
 };
 

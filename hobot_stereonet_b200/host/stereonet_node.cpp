@@ -6,6 +6,7 @@
 #include <unistd.h>
 
 #include <chrono>
+#include <thread>
 
 namespace hobot {
 namespace stereonet {
@@ -39,12 +40,23 @@ StereonetNode::StereonetNode(const std::string& node_name, const Params& params)
   sp_preprocess_ = std::make_shared<PreProcess>("");
   gpu_preprocess_ = param(params, "preprocess", "gpu") != "cpu" && model_input_width_ % 2 == 0 && model_input_height_ % 2 == 0;
   jpeg_on_ = param(params, "jpeg", "on") != "off";
+  {
+    const int hw = (int)std::thread::hardware_concurrency();
+    const int def = hw > 8 ? hw / 2 : 4;
+    jpeg_threads_ = atoi(param(params, "jpeg_threads", std::to_string(def)).c_str());
+    if (jpeg_threads_ < 1) jpeg_threads_ = 1;
+  }
   // the reference's two steps (cv::cvtColor NV12 -> BGR, cv::imencode ".jpg"; stereonet_node.cpp:775-782) restated in the library
   jpeg_encoder_ = [](const uint8_t* nv12, int w, int h, std::vector<uint8_t>& jpeg) {
-    const int64_t n = snb_jpeg_encode_nv12(nv12, w, h, 0, nullptr, 0);
+    jpeg.resize((size_t)w * h * 3 + 4096);                 // one pass: more than any baseline stream of this picture can take
+    int64_t n = snb_jpeg_encode_nv12(nv12, w, h, 0, jpeg.data(), jpeg.size());
+    if (n > (int64_t)jpeg.size()) {                        // (it reports the size it needs, nothing was overrun)
+      jpeg.resize((size_t)n);
+      n = snb_jpeg_encode_nv12(nv12, w, h, 0, jpeg.data(), jpeg.size());
+    }
     if (n <= 0) return false;
     jpeg.resize((size_t)n);
-    return snb_jpeg_encode_nv12(nv12, w, h, 0, jpeg.data(), jpeg.size()) == n;
+    return true;
   };
   ok_ = true;
 }
@@ -131,7 +143,7 @@ void StereonetNode::FeedImg(const HbmMsg1080P& img_msg) {
     bin->w = w; bin->h = h;            // the reference leaves the 1280x720 defaults (stereonet_node.h:43-44)
     if (jpeg_on_ && jpeg_encoder_) {
       // left view of the side-by-side frame (:752-766), then NV12 -> BGR -> JPEG (:775-782).  The encode does not feed
-      // the model, so it runs beside the GPU pass (at most 4 at once; beyond that the feeding thread does it itself).
+      // the model, so it runs beside the GPU pass (jpeg_threads_ at once; beyond that the feeding thread does it itself).
       auto left = std::make_shared<std::vector<uint8_t>>((size_t)w * h * 3 / 2);
       for (int r = 0; r < h * 3 / 2; ++r) memcpy(left->data() + (size_t)r * w, img_msg.data + (size_t)r * img_msg.width, w);
       JpegEncoder enc = jpeg_encoder_;
@@ -141,7 +153,7 @@ void StereonetNode::FeedImg(const HbmMsg1080P& img_msg) {
         --jpeg_inflight_;
         return jpeg;
       };
-      const bool spawn = ++jpeg_inflight_ <= 4;
+      const bool spawn = ++jpeg_inflight_ <= jpeg_threads_;
       bin->jpeg_future = std::async(spawn ? std::launch::async : std::launch::deferred, job).share();
       if (!spawn) bin->jpeg_future.wait();
     }

@@ -106,6 +106,7 @@ class StereonetNode : public hobot::dnn_node::DnnNode {
   bool gpu_preprocess_ = true;
   bool jpeg_on_ = true;
   std::atomic<int> jpeg_inflight_{0};
+  int jpeg_threads_ = 4;               // JPEG encodes running beside the GPU passes (parameter jpeg_threads; default: half the host cores)
   int dropped_ = 0;
 };
 
