@@ -2,33 +2,35 @@
 # Run under gpurun (one GPU): launch list of the bench + full ncu captures of the dominant kernels.
 # usage: tools/profile.sh <tag>
 # Numbers printed by a run under ncu are never bench values; the bench lines come from the plain runs at the end.
+# Launch arithmetic (config 2, K = 3, round-2 pipeline): a pass is 84 launches, all inside the CUDA graph:
+#   k_conv_stream 54 (firstconv.1/.2, layer2 x32, layer3 x6, layer4 x6, head.filter.1-4, conv3d_alone, conv_out x3),
+#   k_resblock_tc 21 (layer1 x3, refine0/1/2 x6), k_refine_head 3, k_conv_tc 2 (lastconv.0, head.filter.0), k_conv1x1 2,
+#   k_conv_first_s8 1, k_costvol 1.  With --no-e2e the bench creates one context: its eager warm-up pass comes first.
 set -u
-TAG=${1:-r01}
+TAG=${1:-r02}
 mkdir -p gpurun_out
-# 1. every launch with its device time (cold cache, serialised: compare SHARES).  The pass is 92 launches; the
-#    library's create-time eager pass comes first, then bench warm-ups and steps.
-ncu --metrics gpu__time_duration.sum --clock-control none -s 96 -c 480 --csv \
-    --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e \
-    > gpurun_out/${TAG}_launches.log 2>&1
-# 2. full captures.  k_resblock_tc: 21 launches per pass (layer1 x3, refine0/1/2 x6); skip the create pass and land on the
-#    full-resolution refinement blocks of the first bench pass.  k_conv_stream: 58 launches per pass (firstconv.1/.2,
-#    layer1.0.downsample, layer2 x33, layer3 x7, layer4 x6, lastconv.1, head.filter.1-4, conv3d_alone, conv_out x3): skip the
-#    create pass + 6 and capture layer2.1.conv_a / conv_b (the shape of 30 launches), then head.filter.1 (3-D).
-ncu --set full --clock-control none --import-source on -k regex:k_resblock_tc -s 36 -c 2 -f -o gpurun_out/${TAG}_resblock \
-    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_resblock.log 2>&1
-ncu -i gpurun_out/${TAG}_resblock.ncu-rep --page raw --csv > gpurun_out/${TAG}_resblock_raw.csv 2>/dev/null
-ncu --set full --clock-control none --import-source on -k regex:k_conv_stream -s 64 -c 2 -f -o gpurun_out/${TAG}_stream \
-    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_stream.log 2>&1
-ncu -i gpurun_out/${TAG}_stream.ncu-rep --page raw --csv > gpurun_out/${TAG}_stream_raw.csv 2>/dev/null
-ncu --set full --clock-control none --import-source on -k regex:k_conv_stream -s 108 -c 1 -f -o gpurun_out/${TAG}_stream3d \
-    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_stream3d.log 2>&1
-ncu -i gpurun_out/${TAG}_stream3d.ncu-rep --page raw --csv > gpurun_out/${TAG}_stream3d_raw.csv 2>/dev/null
-ncu --set full --clock-control none --import-source on -k regex:k_costvol -s 1 -c 1 -f -o gpurun_out/${TAG}_costvol \
-    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_costvol.log 2>&1
-ncu -i gpurun_out/${TAG}_costvol.ncu-rep --page raw --csv > gpurun_out/${TAG}_costvol_raw.csv 2>/dev/null
-# 3. plain runs: per-op CUDA-event table, bench lines
+B="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e"
+# 1. every launch with its device time (cold cache, serialised: compare SHARES)
+ncu --metrics gpu__time_duration.sum --clock-control none -s 84 -c 420 --csv \
+    --log-file gpurun_out/${TAG}_launches.csv $B > gpurun_out/${TAG}_launches.log 2>&1
+# 2. full captures (skip the create pass, land on the named layers of the first bench pass)
+cap() {   # name, kernel regex, skip, count, bench args
+  ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c $4 -f -o gpurun_out/${TAG}_$1 $5 > gpurun_out/${TAG}_$1.log 2>&1
+  ncu -i gpurun_out/${TAG}_$1.ncu-rep --page raw --csv > gpurun_out/${TAG}_ncu_full_$1.csv 2>/dev/null
+}
+cap resblock k_resblock_tc 36 2 "$B"            # refine.2.blocks.0/.1 (full resolution)
+cap stream k_conv_stream 58 2 "$B"              # layer2.1.conv_a / conv_b: the shape of 30 of the 54 launches
+cap stream3d k_conv_stream 100 1 "$B"           # head.filter.1 (3-D)
+cap refinehead k_refine_head 5 1 "$B"           # full-resolution refinement head (M4/M5 fusion: HBM GB/s)
+cap refinehead0 k_refine_head 3 1 "$B"          # stage-0 head: soft-argmin over D + upsample + conv_in
+cap costvol k_costvol 1 1 "$B"
+# D = 192 (config 4, 4 pairs per pass): cost-volume build and head.filter.0 where the volume no longer fits in L2
+B4="python bench.py --config 4 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e"
+cap costvol_d192 k_costvol 1 1 "$B4"
+cap filter0_d192 k_conv_tc 3 1 "$B4"
+rm -f gpurun_out/${TAG}_*.ncu-rep
+# 3. plain runs: per-op CUDA-event table, role counters
 python tools/opprof.py --precision tc > gpurun_out/${TAG}_opprof.txt 2>&1
+python tools/opprof.py --precision tc --batch 8 > gpurun_out/${TAG}_opprof_b8.txt 2>&1
 SNB_TC_PROF=1 python tools/opprof.py --precision tc --reps 1 2>&1 | grep -E "rbprof|csprof|tcprof" > gpurun_out/${TAG}_roleprof.txt
-python bench.py --steps 50 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_reference_bench.json 2>> gpurun_out/${TAG}_bench.err
-ls -la gpurun_out/ | tail -30
+ls -la gpurun_out/ | grep ${TAG}_ | tail -30
