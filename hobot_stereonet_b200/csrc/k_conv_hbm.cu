@@ -310,7 +310,7 @@ namespace snb {
 // channel blocks (exact hi + lo -> fp32) and keeps COUT fp32 accumulators, with the weights broadcast from shared memory.
 template <int COUT>
 __global__ void __launch_bounds__(128) k_conv1x1(const Conv1x1Params p) {
-  extern __shared__ float s_w[];                 // [cin][COUT]
+  extern __shared__ __align__(16) float s_w[];   // [cin][COUT]
   pdl_trigger();
   for (int i = threadIdx.x; i < p.cbin * 8 * COUT; i += 128) s_w[i] = p.wgt[i];    // constants of the pass: before the wait
   pdl_wait();
@@ -328,7 +328,11 @@ __global__ void __launch_bounds__(128) k_conv1x1(const Conv1x1Params p) {
 #pragma unroll
     for (int e = 0; e < 8; ++e)
 #pragma unroll
-      for (int co = 0; co < COUT; ++co) acc[co] = fmaf(v[e], s_w[(cb * 8 + e) * COUT + co], acc[co]);
+      for (int co = 0; co < COUT; co += 4) {        // one 128-bit broadcast load feeds four FMAs (the scalar version was LDS-issue bound)
+        const float4 w4 = *reinterpret_cast<const float4*>(&s_w[(cb * 8 + e) * COUT + co]);
+        acc[co] = fmaf(v[e], w4.x, acc[co]); acc[co + 1] = fmaf(v[e], w4.y, acc[co + 1]);
+        acc[co + 2] = fmaf(v[e], w4.z, acc[co + 2]); acc[co + 3] = fmaf(v[e], w4.w, acc[co + 3]);
+      }
   }
   const size_t obase = (size_t)n * p.out.ss + ((size_t)y * p.out.ws + x) * 8;
 #pragma unroll
