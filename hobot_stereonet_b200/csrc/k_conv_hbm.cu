@@ -309,19 +309,21 @@ namespace snb {
 // tensor kernel they cost 9x the MMAs and a full pipeline start (15-18 us each); here one thread owns one pixel, walks its input
 // channel blocks (exact hi + lo -> fp32) and keeps COUT fp32 accumulators, with the weights broadcast from shared memory.
 template <int COUT>
-__global__ void __launch_bounds__(128) k_conv1x1(const Conv1x1Params p) {
+__global__ void __launch_bounds__(64) k_conv1x1(const Conv1x1Params p) {
   extern __shared__ __align__(16) float s_w[];   // [cin][COUT]
   pdl_trigger();
-  for (int i = threadIdx.x; i < p.cbin * 8 * COUT; i += 128) s_w[i] = p.wgt[i];    // constants of the pass: before the wait
+  for (int i = threadIdx.x; i < p.cbin * 8 * COUT; i += 64) s_w[i] = p.wgt[i];     // constants of the pass: before the wait
   pdl_wait();
   __syncthreads();
-  const int idx = blockIdx.x * 128 + threadIdx.x, n = blockIdx.y;
+  const int idx = blockIdx.x * 64 + threadIdx.x, n = blockIdx.y;
   if (idx >= p.h * p.w) return;
   const int y = idx / p.w, x = idx - y * p.w;
   float acc[COUT];
 #pragma unroll
   for (int co = 0; co < COUT; ++co) acc[co] = __ldg(p.bias + co);
   const size_t ibase = (size_t)n * p.in.ss + ((size_t)y * p.in.ws + x) * 8;
+  // 16 K pixels at most: the kernel is latency-bound, so small CTAs (every SM gets a few) and four channel blocks of loads in flight
+#pragma unroll 4
   for (int cb = 0; cb < p.cbin; ++cb) {
     float v[8];
     St<__half>::ld8(p.in.p, ibase + (size_t)cb * p.in.slice, p.in.lo, v);
@@ -352,10 +354,10 @@ void conv1x1_pack(const float* W, int cout, int cin, int cbin, std::vector<float
 }
 
 cudaError_t launch_conv1x1(Conv1x1Params p, int cout, int N, cudaStream_t st) {
-  const dim3 g(cdiv(p.h * p.w, 128), N);
+  const dim3 g(cdiv(p.h * p.w, 64), N);
   const size_t smem = (size_t)p.cbin * 8 * cout * sizeof(float);
-  if (cout == 16) return launch_k(k_conv1x1<16>, g, 128, smem, st, p);
-  if (cout == 32) return launch_k(k_conv1x1<32>, g, 128, smem, st, p);
+  if (cout == 16) return launch_k(k_conv1x1<16>, g, 64, smem, st, p);
+  if (cout == 32) return launch_k(k_conv1x1<32>, g, 64, smem, st, p);
   return cudaErrorInvalidValue;
 }
 
