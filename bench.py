@@ -157,11 +157,18 @@ class ClockSampler:
                 "samples": len(self.sm), "how": self.how}
 
 
-def ncu_traffic(kernel: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, read from the newest committed `ncu --set full`
-    raw page under profiles/ that holds launches of it (None when no capture names the kernel)."""
+def ncu_traffic(kernel: str, d192: bool = False):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, averaged over the launches captured in the newest
+    round's committed `ncu --set full` raw pages under profiles/ (captures of the D = 192 configuration are used for the D = 192
+    configurations only).  None when no capture names the kernel."""
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*ncu_full*.csv")), reverse=True):
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*ncu_full*.csv")), reverse=True)
+    files = [f for f in files if ("_d192" in os.path.basename(f)) == d192]
+    newest = os.path.basename(files[0]).split("_")[0] if files else ""
+    vals, used = [], []
+    for path in files:
+        if not os.path.basename(path).startswith(newest + "_"):
+            continue
         try:
             rows = list(csv.reader(open(path, newline="")))
             hdr = rows[0]
@@ -169,10 +176,13 @@ def ncu_traffic(kernel: str):
         except (OSError, ValueError, IndexError):
             continue
         ur, uw = unit.get(rows[1][ir], 1.0), unit.get(rows[1][iw], 1.0)
-        vals = [float(r[ir]) * ur + float(r[iw]) * uw for r in rows[2:] if len(r) > max(ir, iw) and kernel in r[ik]]
-        if vals:
-            return {"bytes_per_launch": float(np.mean(vals)), "launches_captured": len(vals), "source": os.path.relpath(path, ROOT)}
-    return None
+        v = [float(r[ir]) * ur + float(r[iw]) * uw for r in rows[2:] if len(r) > max(ir, iw) and kernel in r[ik]]
+        if v:
+            vals += v
+            used.append(os.path.relpath(path, ROOT))
+    if not vals:
+        return None
+    return {"bytes_per_launch": float(np.mean(vals)), "launches_captured": len(vals), "source": used}
 
 
 # ---- CPU legs (the only code that may touch oracle/) ------------------------------------------------------------------
@@ -503,7 +513,7 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
         fam_of = lambda n: ("k_resblock_tc" if "[tc-block]" in n else "k_conv_stream" if "[tc-stream]" in n else
                             "k_conv_tc" if "[tc]" in n else "k_costvol" if n == "costvol" else
-                            "k_softargmin_refine" if n.startswith("softargmin") else "cuda_core_and_hbm")
+                            "k_refine_head" if ".head [" in n else "cuda_core_and_hbm")
         fam = {}
         for n, v in prof.items():
             a = fam.setdefault(fam_of(n), [0.0, 0.0, 0.0, 0])
@@ -514,12 +524,12 @@ def main():
         d = fam[dom]
         tf = lambda v: v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0.0
         gbs = lambda v: v[2] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else 0.0
-        traffic = ncu_traffic(dom)
+        traffic = ncu_traffic(dom, d192=D >= 96)
         hbm = {}
-        for k in ("k_costvol", "k_softargmin_refine"):
+        for k in ("k_costvol", "k_refine_head"):      # the two HBM-bound kernels north_star names: cost-volume build, soft-argmin + upsample + refinement input
             if k in fam:
                 hbm[k] = {"bound": "hbm", "achieved": gbs(fam[k]), "peak": hbm_peak, "unit": "GB/s", "frac": gbs(fam[k]) / hbm_peak,
-                          "algorithmic_bytes_per_launch": fam[k][2] / max(fam[k][3], 1), "traffic": (ncu_traffic(k.replace("_refine", "")) or {}).get("bytes_per_launch")}
+                          "algorithmic_bytes_per_launch": fam[k][2] / max(fam[k][3], 1), "traffic": (ncu_traffic(k, d192=D >= 96) or {}).get("bytes_per_launch")}
         roofline = {"kernel": dom, "bound": "tensor", "achieved": tf(d), "peak": tf_peak, "unit": "TFLOP/s", "frac": tf(d) / tf_peak,
                     # split-fp16 operands: 3 fp16 MMAs are issued per algorithmic MAC, so the tensor pipe works at 3 x frac
                     "fp16_mma_issued_frac": 3 * tf(d) / tf_peak,
