@@ -212,6 +212,16 @@ struct CsParams {        // k_conv_stream.cu: streaming convolution, one 32-chan
 };
 struct CsPlan { CsParams p; size_t smem; int num_sms; };
 
+struct Cost3dParams {    // k_cost3d.cu: Conv3d 32 -> 1 (conv3d_alone) with every input row read once
+  TV in;                 // split-fp16 C8 [n][4][D][h][w]
+  const __half* w; float* out;      // out: fp32 plane [n][D][H][W]
+  float bias, wsc, rzk;
+  int N, D, H, W, strips;
+  int rpb, nband, dps, nseg, total_units, nxs;    // rows per band, depths per segment
+  uint32_t sub_bytes, slot_bytes, w_bytes, p_bytes;
+};
+struct Cost3dPlan { Cost3dParams p; int num_sms; };
+
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 // ---- compensation of the tensor core's round-toward-zero accumulation ------------------------------------------------

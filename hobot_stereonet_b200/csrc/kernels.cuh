@@ -45,6 +45,12 @@ cudaError_t launch_conv_first_s8(ConvFirstS8Params p, const IoPtrs& io, int B, c
 void refine_head_pack(const float* W, const float* bias, RefineHeadParams* p);
 cudaError_t launch_refine_head(RefineHeadParams p, const IoPtrs& io, int B, cudaStream_t st);
 
+// k_cost3d.cu — head.conv3d_alone (Conv3d 32 -> 1) for large volumes: all nine (depth tap, kernel row) products of an input row in one
+// N = 32 MMA, every input row read once (the streaming kernel reads it for each of the three output depths it feeds)
+void cost3d_pack_weights(const float* W, int cin, int wlog2, std::vector<__half>& out);
+cudaError_t cost3d_plan(Cost3dPlan* plan, const Tens& in, int num_sms);
+cudaError_t launch_cost3d(const Cost3dPlan& plan, int N, const void* w, int wlog2, float bias, float* out, cudaStream_t st);
+
 // stand-alone 1x1 convolutions (layer1.0's shortcut, lastconv.1): CUDA cores, one pixel per thread
 void conv1x1_pack(const float* W, int cout, int cin, int cbin, std::vector<float>& out);
 cudaError_t launch_conv1x1(Conv1x1Params p, int cout, int N, cudaStream_t st);

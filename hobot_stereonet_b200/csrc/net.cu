@@ -427,7 +427,28 @@ struct Builder {
       const float* rup = res_up ? res_up->p : nullptr;
       const int qH = c->H, qW = c->W;
       const float qmul = c->qmul;
-      op.fn = [splan, dw, wl, bias, op_, has_res, rt, rl, rup, emit_q, qH, qW, qmul](int B, const IoPtrs& io, cudaStream_t st) {
+      // Conv3d 32 -> 1 on a large volume (many pairs per pass or many hypotheses): the read-once kernel (k_cost3d.cu); small volumes
+      // cannot be cut into >= one unit per SM without giving the saving back as halo, they stay on the streaming kernel
+      Cost3dPlan c3{};
+      const __half* dw3 = nullptr;
+      static const int c3_min_rows = getenv("SNB_COST3D_MIN_ROWS") ? atoi(getenv("SNB_COST3D_MIN_ROWS")) : 8192;
+      if (cw.kz == 3 && cw.cin == 32 && !res_c8 && !res_up && !relu && !emit_q && cost3d_plan(&c3, in, c->num_sms) == cudaSuccess) {
+        const int key3 = 300;
+        if (!cw.w_tc.count(key3)) {
+          std::vector<__half> packed;
+          cost3d_pack_weights(c->wts[name + ".weight"].data.data(), cw.cin, cw.wlog2, packed);
+          __half* d3 = nullptr;
+          if (cudaMalloc(&d3, packed.size() * sizeof(__half)) != cudaSuccess) { fail = true; return out; }
+          cudaMemcpy(d3, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice);
+          c->wallocs.push_back(d3);
+          cw.w_tc[key3] = d3;
+        }
+        dw3 = cw.w_tc[key3];
+      }
+      const float b0 = cw.b0;
+      const long rows_per_pair = (long)in.d * in.h;
+      op.fn = [splan, dw, wl, bias, op_, has_res, rt, rl, rup, emit_q, qH, qW, qmul, c3, dw3, b0, rows_per_pair](int B, const IoPtrs& io, cudaStream_t st) {
+        if (dw3 && rows_per_pair * B >= c3_min_rows) return launch_cost3d(c3, B, dw3, wl, b0, op_, st);
         return launch_conv_stream(splan, B, dw, wl, bias, nullptr, has_res ? &rt : nullptr, op_, rup, 1, rl, 1, st, 3, emit_q ? &io : nullptr, qH, qW,
                                   qmul);
       };

@@ -53,13 +53,14 @@ def test_blob_container_agrees_with_oracle_and_library(built_lib):
         weights_io.read_blob(b"NOTABLOB" + blob[8:])
 
 
-def _synthetic_checkpoint(K, seed, style):
-    """conv (no bias) + BatchNorm for every layer, named the way `style` says."""
+def _synthetic_checkpoint(K, seed, style, gains=False):
+    """conv (no bias) + BatchNorm for every layer, named the way `style` says.  gains: scale every layer like the seeded blob
+    (oracle/arch.py ConvSpec.gain), so that activations stay O(1) through the 25 residual blocks as in a trained network."""
     rng = np.random.default_rng(seed)
     folded_ref = {}
     sd = {}
     for s in arch.conv_specs(K):
-        w = (rng.standard_normal((s.cout, s.cin) + tuple(s.k)) * np.sqrt(2.0 / (s.cin * np.prod(s.k)))).astype(np.float32)
+        w = (rng.standard_normal((s.cout, s.cin) + tuple(s.k)) * np.sqrt(2.0 / (s.cin * np.prod(s.k))) * (s.gain if gains else 1.0)).astype(np.float32)
         gamma, beta = (rng.random(s.cout) + 0.5).astype(np.float32), (rng.standard_normal(s.cout) * 0.05).astype(np.float32)
         mean, var = (rng.standard_normal(s.cout) * 0.1).astype(np.float32), (rng.random(s.cout) + 0.5).astype(np.float32)
         conv, bn = {"seq": (s.name + ".0", s.name + ".1"), "named": (s.name + ".conv", s.name + ".bn")}[style]
@@ -129,3 +130,33 @@ def test_import_cli_lists_expected_layers(built_lib):
     specs = arch.conv_specs(4)
     assert len(lines) == len(specs)
     assert lines[0] == "backbone.firstconv.0 32x3x3x3" and lines[-1].startswith("head.refine.3.conv_out 1x32x3x3")
+
+
+@pytest.mark.gpu
+def test_imported_checkpoint_runs_on_gpu_like_the_oracle(built_lib, tmp_path):
+    """SURVEY.md §8f rank 4 on the GPU: a conv + BatchNorm checkpoint goes through tools/import_weights.py, the resulting
+    model_file drives both the CPU oracle and the tensor-core path (weights of another distribution than the seeded He-normal
+    blob: per-channel BatchNorm scales, non-zero folded biases), and the two agree to the parity bar."""
+    from hobot_stereonet_b200 import Model, capi
+    from oracle import prepost_ref as pp, synth
+    from oracle.stereonet_ref import Oracle
+    K, H, W, D = 3, 96, 160, 8
+    sd, _ = _synthetic_checkpoint(K, 21, "named", gains=True)
+    ck = tmp_path / "ck.pth"
+    torch.save({"state_dict": {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}}, ck)
+    out = tmp_path / "model.snb"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "import_weights.py"), "--checkpoint", str(ck), "--K", str(K), "--out", str(out)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    blob = out.read_bytes()
+    capi.weights_validate(blob, K)
+    cfg = arch.Config(H, W, K, D)
+    frame = synth.frame(H, W, cfg.max_disp, seed=4)
+    s8 = pp.cvt_nv12_to_tensor_fast(*pp.split_side_by_side_nv12(frame, H, 2 * W), W, H)
+    ref = Oracle(cfg, weights.from_blob(blob)[1]).forward_px(s8)
+    m = Model(H, W, K, D, model_file=str(out), precision=capi.PREC_TC_F16X2)
+    q = m.infer(s8)
+    m.close()
+    err = np.abs(q[:, 0].astype(np.float64) * arch.OUT_SCALE * arch.OUT_NORM - ref)
+    print(f"imported checkpoint: mean EPE {err.mean():.3e} px, max {err.max():.3e} px; disparity range {ref.min():.2f}..{ref.max():.2f} px")
+    assert np.isfinite(ref).all() and err.mean() <= 1e-3 and err.max() <= 2e-2
