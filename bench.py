@@ -511,7 +511,7 @@ def main():
         tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)       # kernel timed inside a long step
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-        fam_of = lambda n: ("k_resblock_tc" if "[tc-block]" in n else "k_conv_stream" if "[tc-stream]" in n else
+        fam_of = lambda n: ("k_resblock_tc" if "[tc-block]" in n else "k_conv_stream" if "[tc-stream" in n else "k_cost3d" if "[tc-cost3d]" in n else
                             "k_conv_tc" if "[tc]" in n else "k_costvol" if n == "costvol" else
                             "k_refine_head" if ".head [" in n else "cuda_core_and_hbm")
         fam = {}
@@ -519,7 +519,7 @@ def main():
             a = fam.setdefault(fam_of(n), [0.0, 0.0, 0.0, 0])
             a[0] += v[0] * scale; a[1] += v[1]; a[2] += v[2]; a[3] += 1
         total_ms = sum(v[0] for v in fam.values())
-        tc_fams = {k: v for k, v in fam.items() if k in ("k_resblock_tc", "k_conv_stream", "k_conv_tc") or args.precision != "tc"}
+        tc_fams = {k: v for k, v in fam.items() if k in ("k_resblock_tc", "k_conv_stream", "k_conv_tc", "k_cost3d") or args.precision != "tc"}
         dom = max(tc_fams, key=lambda k: tc_fams[k][0])
         d = fam[dom]
         tf = lambda v: v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0.0

@@ -1,5 +1,5 @@
-// head.conv3d_alone for LARGE volumes (the last layer of the 3-D aggregation: Conv3d 32 -> 1, 3x3x3):
-// every input row is read ONCE.
+// head.conv3d_alone (the last layer of the 3-D aggregation: Conv3d 32 -> 1, 3x3x3): every input row is
+// read ONCE.
 //
 // The streaming kernel (k_conv_stream, NCO = 16) walks one output depth at a time: an input row (d', y) is fetched by the three
 // output depths it feeds, the layer moves 3 x its input through L2 and is bound by that traffic (D = 192, 4 pairs: 0.84 ms for

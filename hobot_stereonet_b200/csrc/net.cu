@@ -422,16 +422,17 @@ struct Builder {
       const Tens rt = res_c8 ? *res_c8 : Tens();
       const int rl = relu ? 1 : 0;
       float* op_ = out.p;
-      Op op; op.name = name + " [tc-stream]";
+      Op op; op.name = name + (cw.kz == 3 && cw.cin == 32 && !res_c8 && !res_up && !relu && !emit_q ? " [tc-cost3d]" : " [tc-stream]");
       const int wl = cw.wlog2;
       const float* rup = res_up ? res_up->p : nullptr;
       const int qH = c->H, qW = c->W;
       const float qmul = c->qmul;
-      // Conv3d 32 -> 1 on a large volume (many pairs per pass or many hypotheses): the read-once kernel (k_cost3d.cu); small volumes
-      // cannot be cut into >= one unit per SM without giving the saving back as halo, they stay on the streaming kernel
+      // Conv3d 32 -> 1 (conv3d_alone): the read-once kernel (k_cost3d.cu).  Measured against the streaming kernel at config 2:
+      // 22 vs 30 us at one pair per pass, 120 vs 215 us at eight; D = 192, four pairs: 333 vs 623 us - and its shorter
+      // accumulator chains leave less truncation bias in the cost tensor (SNB_COST3D_MIN_ROWS=<huge> restores the streaming kernel)
       Cost3dPlan c3{};
       const __half* dw3 = nullptr;
-      static const int c3_min_rows = getenv("SNB_COST3D_MIN_ROWS") ? atoi(getenv("SNB_COST3D_MIN_ROWS")) : 8192;
+      static const int c3_min_rows = getenv("SNB_COST3D_MIN_ROWS") ? atoi(getenv("SNB_COST3D_MIN_ROWS")) : 0;
       if (cw.kz == 3 && cw.cin == 32 && !res_c8 && !res_up && !relu && !emit_q && cost3d_plan(&c3, in, c->num_sms) == cudaSuccess) {
         const int key3 = 300;
         if (!cw.w_tc.count(key3)) {
