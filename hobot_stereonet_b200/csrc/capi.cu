@@ -75,8 +75,9 @@ int snb_create(snb_ctx** out, const snb_config* cfg) {
   *out = nullptr;
   if (cfg->height <= 0 || cfg->width <= 0)
     return fail(nullptr, SNB_ERR_INVALID, "snb_create: height and width must be positive");
-  if (cfg->K < 1 || cfg->K > 5 || cfg->D < 1 || cfg->D > 512 || cfg->max_batch < 1)
-    return fail(nullptr, SNB_ERR_INVALID, "snb_create: need 1<=K<=5, 1<=D<=512, max_batch>=1");
+  // the backbone reduces by 4 (K = 2), 8 (K = 3) or 16 (K = 4) - layer_strides() in layers.h - and the cost volume sits at 1 / 2^K
+  if (cfg->K < 2 || cfg->K > 4 || cfg->D < 1 || cfg->D > 512 || cfg->max_batch < 1)
+    return fail(nullptr, SNB_ERR_INVALID, "snb_create: need 2<=K<=4, 1<=D<=512, max_batch>=1");
   if (cfg->precision != SNB_PREC_FP32 && cfg->precision != SNB_PREC_TC_F16X2)
     return fail(nullptr, SNB_ERR_INVALID, "snb_create: unknown precision");
 

@@ -60,7 +60,7 @@ enum {
 typedef struct snb_config {
   int32_t struct_size;      /* = sizeof(snb_config) */
   int32_t height, width;    /* valid model input H x W (one view) */
-  int32_t K;                /* x2 refinement stages == log2(cost-volume stride); deployed model: 4 */
+  int32_t K;                /* x2 refinement stages == log2(cost-volume stride), 2..4; deployed model: 4 */
   int32_t D;                /* disparity hypotheses at cost-volume resolution; deployed model: 12 */
   int32_t max_batch;        /* stereo pairs processed per pass; larger calls are chunked */
   int32_t device;           /* CUDA ordinal */

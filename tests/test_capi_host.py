@@ -96,6 +96,10 @@ def test_create_checks_model_file_first(built_lib):
     with pytest.raises(SnbError) as e:
         Model(0, 96, 3, 8, weights=b"x" * 64)
     assert e.value.code == capi.SNB_ERR_INVALID
+    for K in (1, 5):                        # the backbone's stride schedule exists for 1/4, 1/8 and 1/16 volumes only
+        with pytest.raises(SnbError) as e:
+            Model(64, 96, K, 8, weights=b"x" * 64)
+        assert e.value.code == capi.SNB_ERR_INVALID and "2<=K<=4" in str(e.value)
 
 
 def test_synthesized_blob_matches_oracle_layer_table(built_lib):
