@@ -15,17 +15,23 @@
 //                 MMAs into one 96-column accumulator were measured 25 % slower: each re-reads the 4 KB A tile and
 //                 the job becomes shared-memory-bandwidth-bound.)
 //   halo          only 4 extra rows at the top of a column walk (two per conv) instead of 2 per 6-row tile twice.
-//   epilogue      two warp groups, one per conv, so the y emission and the output emission overlap:
-//                 group A (warps 2-5) drains a-jobs, keeps two partial y rows in fp32 registers; a finished row gets
+//   epilogue      two warp groups of EIGHT warps, one per conv, so the y emission and the output emission overlap; a warp
+//                 owns a TMEM lane quarter (32 pixels) and one 16-channel half (four warps per group left a chain of six
+//                 TMEM round trips per thread and job: 61 -> 57 us at 544x960).
+//                 group A (warps 2-9) drains a-jobs, keeps two partial y rows in fp32 registers; a finished row gets
 //                 ReLU, zero outside the image (conv_b's zero padding), hi/lo fp16 split, and goes into the y ring
-//                 in the A-operand layout.  Group B (warps 6-9) drains b-jobs; a finished output row gets the
+//                 in the A-operand layout.  Group B (warps 10-17) drains b-jobs; a finished output row gets the
 //                 residual, ReLU, the split, and goes to HBM.  Biases are added when a partial row is born.
-//   pipeline      warp 0: bulk-copy producer (weights once, then one x row per a-job), warp 1: TMEM owner + MMA
-//                 issuer.  TMEM: conv_a has one 192-column slot (main | corr; a-jobs and b-jobs alternate on the
-//                 tensor pipe, so its drain overlaps the following b-job); conv_b, whose drain carries the residual
-//                 and the HBM stores, has two 96-column slots with hi*hi + hi*lo + lo*hi merged in one accumulator
-//                 (three N = 96 MMAs per tap: +10 % tensor time for the b-jobs, but the issuer no longer waits for
-//                 the slot).
+//   pipeline      warp 0: bulk-copy producer (weights once, then one x row per a-job); warp 1: TMEM owner + issuer of
+//                 conv_a's MMAs; warp 18: issuer of conv_b's MMAs (one issuing thread left a ~300-cycle bubble between
+//                 jobs: barrier polls + commits against a tensor-pipe queue of a few MMAs).
+//                 TMEM: conv_a has one 192-column slot (main | corr; its drain overlaps the b-job in flight); conv_b, whose
+//                 drain carries the residual and the HBM stores, has two 96-column slots with hi*hi + hi*lo + lo*hi
+//                 merged in one accumulator (three N = 96 MMAs per tap: +10 % tensor time for the b-jobs).
+//   shared memory is the binding resource: an M = 128 MMA reads its 4 KB A tile and N x 32 B of weights from shared memory at
+//                 128 B/cycle - cost max(N/2, 32 + N/4) cycles, i.e. N = 96 is shared-memory-bound (56 = 7 KB / 128) and
+//                 N = 192 tensor-bound (96 vs 80).  A row costs 1920 MMA cycles + 2 x 130 cycles of x / y row writes against
+//                 ~2800 measured; more TMEM slots for conv_a make it worse (see launch_resblock_tc).
 //                 Persistent over (sample, strip, comb, row-chunk) units.
 #include <stdlib.h>
 
@@ -39,14 +45,14 @@ namespace snb {
 
 using namespace ptx;
 
-constexpr int RB_THREADS = 320;
-constexpr int RB_GROUP_WARPS = 4;
+constexpr int RB_THREADS = 608;
+constexpr int RB_GROUP_WARPS = 8;                       // per epilogue group: TMEM lane quarter (warp & 3) x 16-channel half
+constexpr int RB_ISSUER_B = 2 + 2 * RB_GROUP_WARPS;     // warp 18: issues conv_b's MMAs (warp 1 issues conv_a's)
 constexpr int RB_SLOT_COLS = 192;                       // [main | corr] x [half][ky][16 ch]
 constexpr int RB_WROWS = 192;                           // packed weight rows per (k16, kx, chunk): [W_hi 96 | W_lo 96]
 constexpr uint32_t RB_W_BYTES = 2 * 3 * 2 * RB_WROWS * 16;   // one conv: [k16][kx][chunk][192 rows][8 halfs]
-constexpr int RB_YSLOTS = 3, RB_ASLOTS = 1, RB_BSLOTS = 2;
-constexpr int RB_BCOLS = 96;                            // conv_b: one merged accumulator per job, two slots
-constexpr int RB_BBASE = RB_ASLOTS * RB_SLOT_COLS;      // first TMEM column of the conv_b slots
+constexpr int RB_YSLOTS = 3;
+constexpr int RB_BCOLS = 96;                            // conv_b: one merged accumulator per job
 
 struct RbUnit { int n, x0, c, i0, nr; };
 
@@ -97,8 +103,13 @@ __device__ __forceinline__ void rb_sts16(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-template <bool PROF>
+// AM: conv_a like conv_b (hi*hi, hi*lo, lo*hi chained in ONE 96-column accumulator); AS / BS: TMEM slots of conv_a / conv_b
+template <bool PROF, bool AM, int AS, int BS>
 __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p) {
+  constexpr bool RB_A_MERGED = AM;
+  constexpr int RB_ACOLS = AM ? 96 : 192, RB_ASLOTS = AS, RB_BSLOTS = BS;
+  constexpr int RB_BBASE = RB_ASLOTS * RB_ACOLS;           // first TMEM column of the conv_b slots
+  static_assert(RB_BBASE + RB_BSLOTS * RB_BCOLS <= 512, "TMEM columns");
   extern __shared__ uint8_t smem_raw[];
   __shared__ float s_bias[64];                 // [ba 32 | bb 32]
   __shared__ uint64_t bars[40];
@@ -173,8 +184,16 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
                     &x_full[slot]);
       }
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ================================
+  } else if (warp == 1 || warp == RB_ISSUER_B) {
+    // ================================ MMA issuers ================================
+    // One warp per convolution.  Between two jobs an issuer polls two mbarriers, fences and commits twice (~300 cycles);
+    // the tensor pipe queues only a few MMAs, so with a single issuing thread that gap was a bubble after every job (1280
+    // cycles per 960-cycle job, profiles/r02_roleprof.txt).  Two threads issue into the same pipe: one's gap is covered by
+    // the other's queued MMAs.  conv_a and conv_b are coupled only through the y ring's barriers, as before.
+    // SNB_RB_DEBUG=32 (measurement): warp 1 issues both, in the old interleaved order.
+    const bool one_issuer = (p.dbg & 32) != 0;
+    const bool swap = (p.dbg & 64) != 0;      // measurement: which SM sub-partition issues which convolution
+    const bool do_a = warp == (swap ? RB_ISSUER_B : 1), do_b = one_issuer ? do_a : warp == (swap ? 1 : RB_ISSUER_B);
     const bool leader = elect_one();
     const uint32_t idesc1 = make_idesc_f16(128, RB_SLOT_COLS), idesc2 = make_idesc_f16(128, RB_SLOT_COLS / 2);
     const uint32_t b_lbo = RB_WROWS * 16;
@@ -222,26 +241,28 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
         }
       }
     };
-    uint32_t bs = 0;
+    uint32_t bs = 0, as = 0;
 
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
       const RbUnit un = rb_decode(p, u);
       if (un.nr <= 0) continue;
       for (int step = 0; step < un.nr + 5; ++step) {
-        if (step < un.nr + 4) {                            // a-job: x row i0 - 2 + step
+        if (do_a && step < un.nr + 4) {                    // a-job: x row i0 - 2 + step
           RB_WAIT(tw0, &x_full[xs], xpar);
-          RB_WAIT(tw1, &sa_empty[0], apar);
+          RB_WAIT(tw1, &sa_empty[as], apar);
           tc_fence_after();
           if (leader) {
-            issue_job(x_desc0 + (uint64_t)xs * slot16, wa_desc0, tmem_base);
-            umma_commit(&sa_full[0]);
+            if constexpr (RB_A_MERGED) issue_job_b(x_desc0 + (uint64_t)xs * slot16, wa_desc0, tmem_base + as * RB_ACOLS);
+            else issue_job(x_desc0 + (uint64_t)xs * slot16, wa_desc0, tmem_base + as * RB_ACOLS);
+            umma_commit(&sa_full[as]);
             umma_commit(&x_empty[xs]);
           }
           __syncwarp();
           if (++xs == (uint32_t)p.nxs) { xs = 0; xpar ^= 1; }
-          apar ^= 1; ++njobs;
+          if (++as == RB_ASLOTS) { as = 0; apar ^= 1; }
+          ++njobs;
         }
-        if (step >= 3 && step - 3 < un.nr + 2) {           // b-job: y row i0 - 1 + (step - 3)
+        if (do_b && step >= 3 && step - 3 < un.nr + 2) {   // b-job: y row i0 - 1 + (step - 3)
           RB_WAIT(tw2, &y_full[ys], ypar);
           RB_WAIT(tw3, &sb_empty[bs], bpar);
           tc_fence_after();
@@ -259,22 +280,27 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
     }
     if (PROF && lane == 0) {
       long long* q = p.prof + blockIdx.x * 24;
-      q[0] = clock64() - t_start; q[1] = tw0; q[2] = tw1; q[3] = tw2; q[4] = tw3; q[5] = njobs;
+      if (do_a) { q[0] = clock64() - t_start; q[1] = tw0; q[2] = tw1; q[5] = njobs; }
+      if (do_b) { q[6] = clock64() - t_start; q[3] = tw2; q[4] = tw3; q[7] = njobs; }
     }
   } else if (warp < 2 + RB_GROUP_WARPS) {
     // ================================ epilogue group A: a-jobs -> y rows ================================
+    // Eight warps: a warp owns a TMEM lane quarter (32 pixels) and one 16-channel half.  With four warps doing both halves
+    // the drain of one job was a chain of six TMEM round trips per thread (~1500 cycles per job against 960 of MMAs) on an
+    // SM sub-partition holding two resident epilogue warps; half the chain per warp and twice the warps hide it.
     const int m = (warp & 3) * 32 + lane;     // TMEM lane = M row = pixel within the 128-wide window
-    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const int hf = (warp - 2) >> 2;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + hf * 48;
     const uint32_t sy_addr = smem_u32(s_y) + (uint32_t)m * 16;
-    const float kna = p.rzk * 6.f;            // MMAs per conv_a main accumulator: 2 chunks x 3 kernel columns
+    const float kna = p.rzk * (RB_A_MERGED ? 18.f : 6.f);   // MMAs per conv_a accumulator: 2 chunks x 3 kernel columns (x 3 products)
     uint32_t na = 0, ny = 0;
-    long long t_emit = 0;
+    long long t_emit = 0, t_drain = 0;
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
       const RbUnit un = rb_decode(p, u);
       if (un.nr <= 0) continue;
-      float a0[32], a1[32];
+      float a0[16], a1[16];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) a0[c] = a1[c] = 0.f;
+      for (int c = 0; c < 16; ++c) a0[c] = a1[c] = 0.f;
       const int ypx = un.x0 - d + m;          // image column of this thread's y pixel
       const bool col_ok = ypx >= 0 && ypx < p.W;
       for (int ja = 0; ja < un.nr + 4; ++ja, ++na) {
@@ -286,38 +312,36 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
         if (ja >= 2) RB_WAIT(tw1, &y_empty[ys], ((ny / RB_YSLOTS) & 1) ^ 1);
         const long long c0 = PROF ? clock64() : 0;
         // drain first (the finished row goes to f, the partial rows roll over), hand the slot back, then emit
-        float f[32];
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const uint32_t col = lane_addr + ts * RB_SLOT_COLS + hf * 48;
+        float f[16];
+        {
+          const uint32_t col = lane_addr + ts * RB_ACOLS;
           float v[16];
-          rb_ld_sum(col + 32, v);              // kernel row 2 completes the oldest partial row
+          if constexpr (RB_A_MERGED) rb_ld1(col + 32, v); else rb_ld_sum(col + 32, v);     // kernel row 2 completes the oldest partial row
 #pragma unroll
-          for (int c = 0; c < 16; ++c) f[hf * 16 + c] = a0[hf * 16 + c] + v[c];
-          rb_ld_sum(col + 16, v);
+          for (int c = 0; c < 16; ++c) f[c] = a0[c] + v[c];
+          if constexpr (RB_A_MERGED) rb_ld1(col + 16, v); else rb_ld_sum(col + 16, v);
 #pragma unroll
-          for (int c = 0; c < 16; ++c) a0[hf * 16 + c] = a1[hf * 16 + c] + v[c];
-          rb_ld_sum(col, v);
+          for (int c = 0; c < 16; ++c) a0[c] = a1[c] + v[c];
+          if constexpr (RB_A_MERGED) rb_ld1(col, v); else rb_ld_sum(col, v);
 #pragma unroll
-          for (int c = 0; c < 16; ++c) a1[hf * 16 + c] = v[c] + s_bias[hf * 16 + c];
+          for (int c = 0; c < 16; ++c) a1[c] = v[c] + s_bias[hf * 16 + c];
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sa_empty[ts]);
+        if (PROF) t_drain += clock64() - c0;
         if (ja >= 2) {
 #pragma unroll
-          for (int cb = 0; cb < 4; ++cb) {
+          for (int jb = 0; jb < 2; ++jb) {
             float g[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) g[q] = ok ? fmaxf(rz_comp(f[cb * 8 + q], kna), 0.f) * p.wsa : 0.f;   // truncation loss back (common.cuh), ReLU, out of the weight scale
+            for (int q = 0; q < 8; ++q) g[q] = ok ? fmaxf(rz_comp(f[jb * 8 + q], kna), 0.f) * p.wsa : 0.f;   // truncation loss back (common.cuh), ReLU, out of the weight scale
             uint4 oh, ol;
             rb_split8(g, oh, ol);
-            const uint32_t a = sy_addr + ys * p.slot_bytes + (uint32_t)cb * p.sub_bytes;
+            const uint32_t a = sy_addr + ys * p.slot_bytes + (uint32_t)(hf * 2 + jb) * p.sub_bytes;
             rb_sts16(a, oh);
             rb_sts16(a + 4 * p.sub_bytes, ol);
           }
-        }
-        if (ja >= 2) {
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(&y_full[ys]);
@@ -328,12 +352,13 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
     }
     if (PROF && warp == 2 && lane == 0) {
       long long* q = p.prof + blockIdx.x * 24;
-      q[8] = clock64() - t_start; q[9] = tw0; q[10] = tw1; q[11] = t_emit;
+      q[8] = clock64() - t_start; q[9] = tw0; q[10] = tw1; q[11] = t_emit; q[12] = t_drain;
     }
-  } else {
+  } else if (warp < RB_ISSUER_B) {
     // ================================ epilogue group B: b-jobs -> output rows ================================
     const int m = (warp & 3) * 32 + lane;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + RB_BBASE;
+    const int hf = (warp - (2 + RB_GROUP_WARPS)) >> 2;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + RB_BBASE + hf * 48;
     const __half* res = static_cast<const __half*>(p.res.p);
     __half* out = static_cast<__half*>(p.out.p);
     const float knb = p.rzk * ((p.dbg & 16) ? 12.f : 18.f);      // conv_b merged accumulator: 2 chunks x 3 columns x {hi*hi, hi*lo, lo*hi}
@@ -342,72 +367,66 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
       const RbUnit un = rb_decode(p, u);
       if (un.nr <= 0) continue;
-      float b0[32], b1[32];
+      float b0[16], b1[16];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) b0[c] = b1[c] = 0.f;
+      for (int c = 0; c < 16; ++c) b0[c] = b1[c] = 0.f;
       const int opx = un.x0 + m;              // image column of this thread's output pixel
       const bool col_ok = m < p.OW && opx < p.W;
-      const size_t r_base = (size_t)un.n * p.res.ss + (size_t)opx * 8;
-      const size_t o_base = (size_t)un.n * p.out.ss + (size_t)opx * 8;
+      const size_t r_base = (size_t)un.n * p.res.ss + (size_t)opx * 8 + (size_t)(hf * 2) * p.res.slice;
+      const size_t o_base = (size_t)un.n * p.out.ss + (size_t)opx * 8 + (size_t)(hf * 2) * p.out.slice;
       for (int jb_ = 0; jb_ < un.nr + 2; ++jb_, ++nb) {
         const uint32_t ts = nb % RB_BSLOTS;
         const int io = jb_ - 2;
         const int row = un.c + d * (un.i0 + io);
         const bool ok = col_ok && io >= 0 && row < p.H;
-        uint4 rh[4], rl[4];
+        uint4 rh[2], rl[2];
         if (ok) {                                          // residual prefetch: in flight while the job's MMAs finish
           const __half* rp = res + r_base + (size_t)row * p.res.ws * 8;
 #pragma unroll
-          for (int cb = 0; cb < 4; ++cb) {
-            rh[cb] = __ldg(reinterpret_cast<const uint4*>(rp + (size_t)cb * p.res.slice));
-            rl[cb] = __ldg(reinterpret_cast<const uint4*>(rp + (size_t)cb * p.res.slice + p.res.lo));
+          for (int jb = 0; jb < 2; ++jb) {
+            rh[jb] = __ldg(reinterpret_cast<const uint4*>(rp + (size_t)jb * p.res.slice));
+            rl[jb] = __ldg(reinterpret_cast<const uint4*>(rp + (size_t)jb * p.res.slice + p.res.lo));
           }
         }
         RB_WAIT(tw0, &sb_full[ts], (nb / RB_BSLOTS) & 1);
         tc_fence_after();
         const long long c0 = PROF ? clock64() : 0;
+        const uint32_t col = lane_addr + ts * RB_BCOLS;
+        float v[16];
+        rb_ld1(col + 32, v);
+        if (ok) {
+          __half* op = out + o_base + (size_t)row * p.out.ws * 8;
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const uint32_t col = lane_addr + ts * RB_BCOLS + hf * 48;
-          float v[16];
-          rb_ld1(col + 32, v);
-          if (ok) {
-            __half* op = out + o_base + (size_t)row * p.out.ws * 8;
+          for (int jb = 0; jb < 2; ++jb) {
+            const __half2* h2 = reinterpret_cast<const __half2*>(&rh[jb]);
+            const __half2* l2 = reinterpret_cast<const __half2*>(&rl[jb]);
+            float f[8];
 #pragma unroll
-            for (int jb = 0; jb < 2; ++jb) {
-              const int cb = hf * 2 + jb;
-              const __half2* h2 = reinterpret_cast<const __half2*>(&rh[cb]);
-              const __half2* l2 = reinterpret_cast<const __half2*>(&rl[cb]);
-              float f[8];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 a = __half22float2(h2[j]), b = __half22float2(l2[j]);
-                const int c = jb * 8 + 2 * j;
-                f[2 * j] = fmaxf(fmaf(rz_comp(b0[hf * 16 + c] + v[c], knb), p.wsb, a.x + b.x), 0.f);
-                f[2 * j + 1] = fmaxf(fmaf(rz_comp(b0[hf * 16 + c + 1] + v[c + 1], knb), p.wsb, a.y + b.y), 0.f);
-              }
-              uint4 oh, ol;
-              rb_split8(f, oh, ol);
-              *reinterpret_cast<uint4*>(op + (size_t)cb * p.out.slice) = oh;
-              *reinterpret_cast<uint4*>(op + (size_t)cb * p.out.slice + p.out.lo) = ol;
+            for (int j = 0; j < 4; ++j) {
+              const float2 a = __half22float2(h2[j]), b = __half22float2(l2[j]);
+              const int c = jb * 8 + 2 * j;
+              f[2 * j] = fmaxf(fmaf(rz_comp(b0[c] + v[c], knb), p.wsb, a.x + b.x), 0.f);
+              f[2 * j + 1] = fmaxf(fmaf(rz_comp(b0[c + 1] + v[c + 1], knb), p.wsb, a.y + b.y), 0.f);
             }
-          }
-          rb_ld1(col + 16, v);
-#pragma unroll
-          for (int c = 0; c < 16; ++c) b0[hf * 16 + c] = b1[hf * 16 + c] + v[c];
-          rb_ld1(col, v);
-#pragma unroll
-          for (int c = 0; c < 16; ++c) b1[hf * 16 + c] = v[c] + s_bias[32 + hf * 16 + c];
-          if (hf == 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sb_empty[ts]);
+            uint4 oh, ol;
+            rb_split8(f, oh, ol);
+            *reinterpret_cast<uint4*>(op + (size_t)jb * p.out.slice) = oh;
+            *reinterpret_cast<uint4*>(op + (size_t)jb * p.out.slice + p.out.lo) = ol;
           }
         }
+        rb_ld1(col + 16, v);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) b0[c] = b1[c] + v[c];
+        rb_ld1(col, v);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) b1[c] = v[c] + s_bias[32 + hf * 16 + c];
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sb_empty[ts]);
         if (PROF) t_emit += clock64() - c0;
       }
     }
-    if (PROF && warp == 6 && lane == 0) {
+    if (PROF && warp == 2 + RB_GROUP_WARPS && lane == 0) {
       long long* q = p.prof + blockIdx.x * 24;
       q[16] = clock64() - t_start; q[17] = tw0; q[18] = t_emit;
     }
@@ -449,7 +468,7 @@ cudaError_t launch_resblock_tc(const RbPlan& plan, int N, const void* wa, const 
   p.N = N; p.wa = static_cast<const __half*>(wa); p.wb = static_cast<const __half*>(wb); p.ba = ba; p.bb = bb;
   p.rzk = rz_unit();
   p.wsa = ldexpf(1.f, -wlog2a); p.wsb = ldexpf(1.f, -wlog2b);
-  { static const int dbg = getenv("SNB_RB_DEBUG") ? atoi(getenv("SNB_RB_DEBUG")) : 0; p.dbg = (long)p.H * p.W >= 400000 ? dbg : 0; }
+  { static const int dbg = getenv("SNB_RB_DEBUG") ? atoi(getenv("SNB_RB_DEBUG")) : 0; p.dbg = ((long)p.H * p.W >= 400000 ? dbg : 0) | (dbg & (32 | 64)); }
   // row chunks: about one unit per SM (every unit pays 4 halo rows, but an idle SM pays more), at least 2 rows each
   const int rc_max = cdiv(p.H, p.dil);
   const int columns = N * p.strips * p.dil;                 // independent column walks
@@ -459,34 +478,48 @@ cudaError_t launch_resblock_tc(const RbPlan& plan, int N, const void* wa, const 
   p.rpc = cdiv(rc_max, nchunk);
   p.nchunk = cdiv(rc_max, p.rpc);
   p.total_units = columns * p.nchunk;
+  // Slot configurations (SNB_RB_VARIANT, measurement): 0 = the product; 1 and 2 give conv_a a second TMEM slot (merged
+  // accumulator, or conv_b cut to one slot).  Every configuration that lets a-jobs run ahead is SLOWER (67 vs 57 us at
+  // 544x960): an N = 96 MMA reads 4 KB of A + 3 KB of B per 56 cycles = all 128 B/cycle of shared memory, so with the tensor
+  // pipe never pausing the y-row stores of epilogue group A starve (emit phase 1600 cycles per row in the role profile), y rows
+  // come late and conv_b idles.  profiles/r02_resblock_variants.txt.
+  using Kern = void (*)(const RbParams);
+  static const Kern variants[] = {k_resblock_tc<false, false, 1, 2>, k_resblock_tc<false, true, 2, 2>, k_resblock_tc<false, false, 2, 1>};
+  constexpr int NV = sizeof(variants) / sizeof(variants[0]);
+  static const int variant = getenv("SNB_RB_VARIANT") ? atoi(getenv("SNB_RB_VARIANT")) % NV : 0;
   static bool attr_done[32] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 31]) {
-    cudaFuncSetAttribute(k_resblock_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);   // static shared: 592 B
-    cudaFuncSetAttribute(k_resblock_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    for (int i = 0; i < NV; ++i) cudaFuncSetAttribute(variants[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);   // static shared: 592 B
+    cudaFuncSetAttribute(k_resblock_tc<true, false, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    cudaFuncSetAttribute(k_resblock_tc<true, true, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
     attr_done[dev & 31] = true;
   }
   const int grid = p.total_units < plan.num_sms ? p.total_units : plan.num_sms;
-  static const int prof = getenv("SNB_TC_PROF") ? atoi(getenv("SNB_TC_PROF")) : 0;
+  static const int prof = getenv("SNB_RB_PROF") ? atoi(getenv("SNB_RB_PROF")) : getenv("SNB_TC_PROF") ? atoi(getenv("SNB_TC_PROF")) : 0;
   if (!prof) {
-    launch_k(k_resblock_tc<false>, grid, RB_THREADS, plan.smem, st, p);
+    launch_k(variants[variant], grid, RB_THREADS, plan.smem, st, p);
     return cudaGetLastError();
   }
   // diagnostics only: per-role cycle counters, synchronous read-back, max over CTAs
   static long long* d_prof = nullptr;
   if (!d_prof) cudaMalloc(&d_prof, 256 * 24 * sizeof(long long));
   p.prof = d_prof;
+  if (prof == 2) {           // the instrumented build, timed from outside like the plain one
+    launch_k(variant == 1 ? k_resblock_tc<true, true, 2, 2> : k_resblock_tc<true, false, 1, 2>, grid, RB_THREADS, plan.smem, st, p);
+    return cudaGetLastError();
+  }
   cudaMemsetAsync(d_prof, 0, 256 * 24 * sizeof(long long), st);
-  launch_k(k_resblock_tc<true>, grid, RB_THREADS, plan.smem, st, p);
+  launch_k(variant == 1 ? k_resblock_tc<true, true, 2, 2> : k_resblock_tc<true, false, 1, 2>, grid, RB_THREADS, plan.smem, st, p);
   cudaStreamSynchronize(st);
   std::vector<long long> h(grid * 24);
   cudaMemcpy(h.data(), d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
   long long mx[24] = {0};
   for (int b = 0; b < grid; ++b) for (int k = 0; k < 24; ++k) mx[k] = std::max(mx[k], h[b * 24 + k]);
-  fprintf(stderr, "[rbprof] H%d W%d dil%d N%d units %d (rpc %d) grid %d | issuer total %lld wait_x %lld wait_slot(a) %lld wait_y %lld wait_slot(b) %lld jobs %lld | "
-          "groupA total %lld wait_full %lld wait_y_empty %lld drain+emit %lld | groupB total %lld wait_full %lld drain+emit %lld\n",
-          p.H, p.W, p.dil, N, p.total_units, p.rpc, grid, mx[0], mx[1], mx[2], mx[3], mx[4], mx[5], mx[8], mx[9], mx[10], mx[11],
+  fprintf(stderr, "[rbprof] H%d W%d dil%d N%d units %d (rpc %d) grid %d | issuer(a) total %lld wait_x %lld wait_slot(a) %lld jobs %lld issuer(b) total %lld wait_y %lld wait_slot(b) %lld | "
+          "groupA total %lld wait_full %lld wait_y_empty %lld drain+emit %lld (drain %lld) | groupB total %lld wait_full %lld drain+emit %lld\n",
+          p.H, p.W, p.dil, N, p.total_units, p.rpc, grid, mx[0], mx[1], mx[2], mx[5], mx[6], mx[3], mx[4], mx[8], mx[9], mx[10], mx[11], mx[12],
           mx[16], mx[17], mx[18]);
   return cudaGetLastError();
 }
