@@ -181,15 +181,17 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_conv_stream(const CsParams
                 umma_f16_acc(dcol, a_hi + 2 * dil16, w_hi + 2 * wkx16, idesc);
                 umma_f16_acc(dcol, a_lo + 2 * dil16, w_hi + 2 * wkx16 + NCOL, idesc);
               } else {
+                // order hi*hi, lo*hi, hi*lo: two consecutive MMAs of one accumulator on the SAME A window cost 68 cycles each
+                // instead of 56 (tools/ubench/mma_two_issuer_bench.cu modes 5 / 8, profiles/r02_ubench_two_issuer.txt)
                 umma_f16(dcol, a_hi, w_hi, idesc, acc);
-                umma_f16_acc(dcol, a_hi, w_hi + NCOL, idesc);
                 umma_f16_acc(dcol, a_lo, w_hi, idesc);
+                umma_f16_acc(dcol, a_hi, w_hi + NCOL, idesc);
                 umma_f16_acc(dcol, a_hi + dil16, w_hi + wkx16, idesc);
-                umma_f16_acc(dcol, a_hi + dil16, w_hi + wkx16 + NCOL, idesc);
                 umma_f16_acc(dcol, a_lo + dil16, w_hi + wkx16, idesc);
+                umma_f16_acc(dcol, a_hi + dil16, w_hi + wkx16 + NCOL, idesc);
                 umma_f16_acc(dcol, a_hi + 2 * dil16, w_hi + 2 * wkx16, idesc);
-                umma_f16_acc(dcol, a_hi + 2 * dil16, w_hi + 2 * wkx16 + NCOL, idesc);
                 umma_f16_acc(dcol, a_lo + 2 * dil16, w_hi + 2 * wkx16, idesc);
+                umma_f16_acc(dcol, a_hi + 2 * dil16, w_hi + 2 * wkx16 + NCOL, idesc);
               }
               umma_commit(&x_empty[slot]);
             }

@@ -234,10 +234,12 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
         for (int kx = 0; kx < 3; ++kx) {
           const uint64_t w_hi = w + (uint64_t)(k16 * 3 + kx) * wkx16, w_lo = w_hi + (uint64_t)RB_BCOLS;
           const uint64_t sh = (uint64_t)(kx * dil16);
+          // order hi*hi, lo*hi, hi*lo: two consecutive MMAs of one accumulator on the SAME A window cost 68 cycles each
+          // instead of 56 (tools/ubench/mma_two_issuer_bench.cu modes 5 / 8) - the b-job was 1230 cycles, not 1008
           if (k16 == 0 && kx == 0) umma_f16_zero(dcol, a_hi, w_hi, idesc2);
           else umma_f16_acc(dcol, a_hi + sh, w_hi, idesc2);
-          umma_f16_acc(dcol, a_hi + sh, w_lo, idesc2);
           if (!no_lo) umma_f16_acc(dcol, a_lo + sh, w_hi, idesc2);
+          umma_f16_acc(dcol, a_hi + sh, w_lo, idesc2);
         }
       }
     };
@@ -294,7 +296,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
     const uint32_t sy_addr = smem_u32(s_y) + (uint32_t)m * 16;
     const float kna = p.rzk * (RB_A_MERGED ? 18.f : 6.f);   // MMAs per conv_a accumulator: 2 chunks x 3 kernel columns (x 3 products)
     uint32_t na = 0, ny = 0;
-    long long t_emit = 0, t_drain = 0;
+    long long t_emit = 0, t_drain = 0, t_fence = 0;
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
       const RbUnit un = rb_decode(p, u);
       if (un.nr <= 0) continue;
@@ -342,7 +344,9 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
             rb_sts16(a, oh);
             rb_sts16(a + 4 * p.sub_bytes, ol);
           }
+          const long long c1 = PROF ? clock64() : 0;
           fence_proxy_async();
+          if (PROF) t_fence += clock64() - c1;
           __syncwarp();
           if (lane == 0) mbar_arrive(&y_full[ys]);
           ++ny;
@@ -352,7 +356,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_resblock_tc(const RbParams p)
     }
     if (PROF && warp == 2 && lane == 0) {
       long long* q = p.prof + blockIdx.x * 24;
-      q[8] = clock64() - t_start; q[9] = tw0; q[10] = tw1; q[11] = t_emit; q[12] = t_drain;
+      q[8] = clock64() - t_start; q[9] = tw0; q[10] = tw1; q[11] = t_emit; q[12] = t_drain; q[13] = t_fence;
     }
   } else if (warp < RB_ISSUER_B) {
     // ================================ epilogue group B: b-jobs -> output rows ================================
@@ -518,8 +522,8 @@ cudaError_t launch_resblock_tc(const RbPlan& plan, int N, const void* wa, const 
   long long mx[24] = {0};
   for (int b = 0; b < grid; ++b) for (int k = 0; k < 24; ++k) mx[k] = std::max(mx[k], h[b * 24 + k]);
   fprintf(stderr, "[rbprof] H%d W%d dil%d N%d units %d (rpc %d) grid %d | issuer(a) total %lld wait_x %lld wait_slot(a) %lld jobs %lld issuer(b) total %lld wait_y %lld wait_slot(b) %lld | "
-          "groupA total %lld wait_full %lld wait_y_empty %lld drain+emit %lld (drain %lld) | groupB total %lld wait_full %lld drain+emit %lld\n",
-          p.H, p.W, p.dil, N, p.total_units, p.rpc, grid, mx[0], mx[1], mx[2], mx[5], mx[6], mx[3], mx[4], mx[8], mx[9], mx[10], mx[11], mx[12],
+          "groupA total %lld wait_full %lld wait_y_empty %lld drain+emit %lld (drain %lld, fence %lld) | groupB total %lld wait_full %lld drain+emit %lld\n",
+          p.H, p.W, p.dil, N, p.total_units, p.rpc, grid, mx[0], mx[1], mx[2], mx[5], mx[6], mx[3], mx[4], mx[8], mx[9], mx[10], mx[11], mx[12], mx[13],
           mx[16], mx[17], mx[18]);
   return cudaGetLastError();
 }

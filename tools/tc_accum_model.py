@@ -89,7 +89,7 @@ def capture_inputs(cfg, s8, wts, names):
 def sample_chain_products(x, w, dil, samples, rng, mode):
     """x [N,C,(D,)H,W] activation (float), w [Cout,C,(kz,)3,3].  Returns per kernel row ky the products of `samples` random
     output elements in the kernels' issue order: list over ky of [steps, 16, S].
-    mode "split": the main accumulator (hi x hi products only); "merged": one accumulator takes hi*hi, hi*lo, lo*hi of every
+    mode "split": the main accumulator (hi x hi products only); "merged": one accumulator takes hi*hi, lo*hi, hi*lo of every
     (chunk, kx) in that order (k_conv_stream with Cin = 32, conv_b of k_resblock_tc); "chain3": hi x hi, a fresh chain per
     16-channel chunk (k_conv_tc), returned as [chunks][3, 16, S]."""
     is3d = w.dim() == 5
@@ -120,8 +120,8 @@ def sample_chain_products(x, w, dil, samples, rng, mode):
                         iw = (co[None, :], ci[:, None], ky, kx)
                     steps.append(xn[ia] * wn[iw])
                     if mode == "merged":
-                        steps.append(xn[ia] * wl[iw])
                         steps.append(xl[ia] * wn[iw])
+                        steps.append(xn[ia] * wl[iw])
         per_ky.append(np.stack(steps))
     return per_ky
 
