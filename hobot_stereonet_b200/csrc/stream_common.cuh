@@ -1,4 +1,4 @@
-// Helpers shared by the streaming tcgen05 convolution kernels (k_conv_stream.cu, k_conv_pipe.cu, k_conv_pair.cu).
+// Helpers of the streaming tcgen05 convolution kernel (k_conv_stream.cu): unit decoding, TMEM drains, the split-fp16 emit.
 #pragma once
 #include "common.cuh"
 #include "tc_ptx.cuh"
