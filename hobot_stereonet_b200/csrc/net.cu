@@ -230,6 +230,34 @@ struct Builder {
     }
     return cw.w_tc[key];
   }
+  // k_conv_stream packing of input channels [c0, c0 + nc) of a convolution (a K split across launches)
+  const __half* stream_weights_part(const std::string& name, ConvW& cw, int c0, int nc) {
+    const int key = 1000 + c0;
+    if (!cw.w_tc.count(key)) {
+      const std::vector<float>& W = c->wts[name + ".weight"].data;
+      const size_t taps = (size_t)cw.kz * cw.ks * cw.ks;
+      std::vector<float> part((size_t)cw.cout * nc * taps);
+      for (int co = 0; co < cw.cout; ++co)
+        std::copy(W.begin() + ((size_t)co * cw.cin + c0) * taps, W.begin() + ((size_t)co * cw.cin + c0 + nc) * taps, part.begin() + (size_t)co * nc * taps);
+      std::vector<__half> packed;
+      cs_pack_weights(part.data(), cw.cout, nc, cw.kz, cw.ks, 32, cw.wlog2, packed);
+      __half* dw = nullptr;
+      if (cudaMalloc(&dw, packed.size() * sizeof(__half)) != cudaSuccess) { fail = true; return nullptr; }
+      cudaMemcpy(dw, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice);
+      c->wallocs.push_back(dw);
+      cw.w_tc[key] = dw;
+    }
+    return cw.w_tc[key];
+  }
+  const float* zero_bias() {
+    if (!zbias) {
+      if (cudaMalloc(&zbias, 32 * sizeof(float)) != cudaSuccess) { fail = true; return nullptr; }
+      cudaMemset(zbias, 0, 32 * sizeof(float));
+      c->wallocs.push_back(zbias);
+    }
+    return zbias;
+  }
+  float* zbias = nullptr;
   bool stream_ok(const ConvW& cw, const Tens& in, int stride, int dil, CsPlan* plan) const {
     if (c->planes != 2 || (c->cfg.flags & (SNB_FLAG_NO_TENSOR | SNB_FLAG_NO_STREAM)) || stride > 2 || (stride == 2 && cw.cout == 1)) return false;
     // input channels as stored (blocks of 8, zero beyond cin) must be whole 16-channel chunks
@@ -356,6 +384,41 @@ struct Builder {
       return out;
     }
     CsPlan splan;
+    static const bool ksplit_ok = !getenv("SNB_STREAM_KSPLIT") || atoi(getenv("SNB_STREAM_KSPLIT"));
+    if (ksplit_ok && cw.kz == 3 && cw.ks == 3 && cw.cin == 64 && cw.cout == 32 && in.cb == 8 && stride == 1 && !res && !stream_ok(cw, in, stride, dil, &splan)) {
+      // head.filter.0 (Conv3d 64 -> 32): its 221 KB weight slice does not fit beside a row ring, but each HALF of the input channels
+      // does - two streaming launches, the second adding the first's output, run at the rate of head.filter.1-4 (428 TFLOP/s at
+      // D = 192 against 299 for the staged tiles of k_conv_tc).  The partial sum passes through the split-fp16 storage (22 bits).
+      ConvW half = cw; half.cin = 32;
+      const Tens in0 = sub_view(in, 0, 4), in1 = sub_view(in, 4, 4);
+      CsPlan p0, p1;
+      if (stream_ok(half, in0, 1, dil, &p0) && stream_ok(half, in1, 1, dil, &p1)) {
+        const __half* w0 = stream_weights_part(name, cw, 0, 32);
+        const __half* w1 = stream_weights_part(name, cw, 32, 32);
+        const float* zb = zero_bias();
+        if (!w0 || !w1 || !zb) return out;
+        const Tens mid = alloc(nmul, cw.cout, in.d, ho, wo, in.pad);
+        const float* bias = cw.b;
+        const int rl = relu ? 1 : 0, wl = cw.wlog2;
+        Op o0 = op, o1 = op;
+        o0.flops = o1.flops = op.flops / 2;
+        o0.bytes = 4.0 * (nmul * (double)in.d * in.h * in.w * 32 + px * out.cb * 8);
+        o1.bytes = 4.0 * (nmul * (double)in.d * in.h * in.w * 32 + 2 * px * out.cb * 8);
+        o0.name += " [tc-stream, input channels 0-31]";
+        o1.name += " [tc-stream, input channels 32-63 + the first half]";
+        o0.fn = [p0, nmul, w0, wl, bias, mid](int B, const IoPtrs&, cudaStream_t st) {
+          return launch_conv_stream(p0, nmul * B, w0, wl, bias, &mid, nullptr, nullptr, nullptr, 0, 0, 1, st);
+        };
+        o1.fn = [p1, nmul, w1, wl, zb, out, mid, rl](int B, const IoPtrs&, cudaStream_t st) {
+          return launch_conv_stream(p1, nmul * B, w1, wl, zb, &out, &mid, nullptr, nullptr, 0, rl, 1, st);
+        };
+        ++c->n_tc_convs;
+        c->ops.push_back(o0);
+        c->ops.push_back(o1);
+        free(mid);
+        return out;
+      }
+    }
     if (stream_ok(cw, in, stride, dil, &splan)) {
       const __half* dw = stream_weights(name, cw, 32);
       if (!dw) return out;
